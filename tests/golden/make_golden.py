@@ -1,0 +1,204 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in the
+authoring container.  Run from the repo root:
+
+    oracle/build_ref.sh && python tests/golden/make_golden.py
+
+The reference cannot travel to the GPU box, the fixtures can.  Every fixture stores the
+INPUTS (tensor data, DRM seeds, TT-DRM cores -- the cores depend on the host's cpu_count(),
+SURVEY.md App. B-3, so they are data, not something to regenerate) and the reference's
+OUTPUTS (DRM entries, Psi/Omega, assembled TT cores).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.ref_import import import_reference  # noqa: E402
+
+ref = import_reference()
+from tt_sketch.drm import SparseGaussianDRM, TensorTrainDRM  # noqa: E402
+from tt_sketch.drm.fast_lazy_gaussian import inds_to_normal  # noqa: E402
+from tt_sketch.sketch import (blocked_stream_sketch, hmt_sketch, orthogonal_sketch,  # noqa: E402
+                              stream_sketch)
+from tt_sketch.tensor import CPTensor, DenseTensor, SparseTensor, TensorSum, TensorTrain  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def gen_lazy_gaussian():
+    rng = np.random.default_rng(12345)
+    out = {}
+    cases = []
+    shapes = [(10, 12, 14, 7), (70000, 70000, 3), (10000, 10000, 10000, 500)]
+    n = 0
+    for shape in shapes:
+        for k in range(1, len(shape) + 1):
+            for (rmin, rmax) in [(0, 17), (5, 17), (12, 17)]:
+                for seed in (5, 179):
+                    nnz = 48
+                    idx = np.stack([rng.integers(0, m, nnz) for m in shape[:k]]).astype(np.int64)
+                    g = np.asarray(inds_to_normal(idx, shape[:k], rmin, rmax, seed))
+                    out[f"c{n}_idx"] = idx
+                    out[f"c{n}_out"] = g
+                    cases.append((len(shape),) + tuple(shape) + (0,) * (4 - len(shape)) + (k, rmin, rmax, seed))
+                    n += 1
+    # deep tails / edge uniforms are covered by test_oracle_pin via scipy.special.ndtri
+    out["cases"] = np.array(cases, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "lazy_gaussian.npz"), **out)
+    print("lazy_gaussian.npz:", n, "cases")
+
+
+def drm_pack(prefix, drm, store):
+    store[prefix + "_seed"] = np.int64(int(drm.seed))
+    store[prefix + "_rank_min"] = np.array(drm.rank_min, dtype=np.int64)  # internal orientation
+    store[prefix + "_rank_max"] = np.array(drm.rank_max, dtype=np.int64)
+    store[prefix + "_true_rank"] = np.array(drm.true_rank, dtype=np.int64)
+    if hasattr(drm, "cores"):
+        for i, c in enumerate(drm.cores):
+            store[prefix + f"_core{i}"] = c
+
+
+def sketch_pack(prefix, Psi, Omega, store):
+    for i, p in enumerate(Psi):
+        store[prefix + f"_Psi{i}"] = p
+    for i, o in enumerate(Omega):
+        store[prefix + f"_Omega{i}"] = o
+
+
+def tensor_pack(prefix, t, store):
+    if isinstance(t, SparseTensor):
+        store[prefix + "_kind"] = np.array("sparse")
+        store[prefix + "_shape"] = np.array(t.shape, dtype=np.int64)
+        store[prefix + "_indices"] = np.asarray(t.indices, dtype=np.int64)
+        store[prefix + "_entries"] = t.entries
+    elif isinstance(t, DenseTensor):
+        store[prefix + "_kind"] = np.array("dense")
+        store[prefix + "_data"] = t.data
+    elif isinstance(t, TensorTrain):
+        store[prefix + "_kind"] = np.array("tt")
+        for i, c in enumerate(t.cores):
+            store[prefix + f"_c{i}"] = c
+    elif isinstance(t, CPTensor):
+        store[prefix + "_kind"] = np.array("cp")
+        for i, c in enumerate(t.cores):
+            store[prefix + f"_c{i}"] = c
+    elif isinstance(t, TensorSum):
+        store[prefix + "_kind"] = np.array("sum")
+        store[prefix + "_n"] = np.int64(len(t.tensors))
+        for i, s in enumerate(t.tensors):
+            tensor_pack(prefix + f"_s{i}", s, store)
+
+
+def make_sparse(shape, nnz, seed):
+    rng = np.random.default_rng(seed)
+    idx = np.stack([rng.integers(0, n, nnz) for n in shape]).astype(np.int64)
+    return SparseTensor(shape, idx, rng.standard_normal(nnz))
+
+
+def gen_sketches():
+    store = {}
+    names = []
+
+    def run(name, tensor, lrank, rrank, ldrm_t, rdrm_t, methods=("stream",), lslices=None, rslices=None):
+        shape = tensor.shape
+        left = ldrm_t(lrank, shape=shape, transpose=False, seed=11)
+        right = rdrm_t(rrank, shape=shape, transpose=True, seed=23)
+        tensor_pack(name + "_T", tensor, store)
+        drm_pack(name + "_L", left, store)
+        drm_pack(name + "_R", right, store)
+        store[name + "_Lkind"] = np.array(ldrm_t.__name__)
+        store[name + "_Rkind"] = np.array(rdrm_t.__name__)
+        store[name + "_lrank"] = np.array(lrank, dtype=np.int64)
+        store[name + "_rrank"] = np.array(rrank, dtype=np.int64)
+        store[name + "_methods"] = np.array(",".join(methods))
+        if "stream" in methods:
+            stt = stream_sketch(tensor, lrank, rrank, left_drm=left, right_drm=right)
+            sketch_pack(name + "_stream", stt.Psi_cores, stt.Omega_mats, store)
+            for i, c in enumerate(stt.C_cores()):
+                store[name + f"_stream_C{i}"] = c
+            # per-bond DRM contractions (operator-level parity for non-sum tensors)
+            if not isinstance(tensor, TensorSum):
+                from tt_sketch.sketch_dispatch import get_sketch_method
+                for i, m in enumerate(get_sketch_method(tensor, left)(tensor)):
+                    store[name + f"_Lc{i}"] = np.ascontiguousarray(m)
+                for i, m in enumerate(get_sketch_method(tensor, right)(tensor)):
+                    store[name + f"_Rc{i}"] = np.ascontiguousarray(m)
+        if "orth" in methods:
+            tt = orthogonal_sketch(tensor, lrank, rrank, left_drm=left, right_drm=right)
+            for i, c in enumerate(tt.cores):
+                store[name + f"_orth_C{i}"] = c
+        if "hmt" in methods:
+            tt = hmt_sketch(tensor, rrank, drm=right)
+            for i, c in enumerate(tt.cores):
+                store[name + f"_hmt_C{i}"] = c
+        if "blocked" in methods:
+            sk = blocked_stream_sketch(tensor, left, right, lslices, rslices)
+            sketch_pack(name + "_blocked", sk.Psi_cores, sk.Omega_mats, store)
+            store[name + "_lslices"] = np.array(lslices, dtype=np.int64)
+            store[name + "_rslices"] = np.array(rslices, dtype=np.int64)
+        names.append(name)
+
+    sp = make_sparse((7, 8, 9, 10), 300, 1)
+    run("sparse_gauss", sp, (3, 4, 5), (5, 6, 7), SparseGaussianDRM, SparseGaussianDRM,
+        methods=("stream", "blocked"),
+        lslices=[(0, 0, 0), (2, 2, 3), (3, 4, 5)], rslices=[(0, 0, 0), (3, 3, 3), (5, 6, 7)])
+    run("sparse_ttdrm", sp, (3, 4, 5), (5, 6, 7), TensorTrainDRM, TensorTrainDRM,
+        methods=("stream", "orth", "hmt", "blocked"),
+        lslices=[(0, 0, 0), (2, 2, 3), (3, 4, 5)], rslices=[(0, 0, 0), (3, 3, 3), (5, 6, 7)])
+    run("sparse_mixed", sp, (6, 7, 8), (3, 4, 5), TensorTrainDRM, SparseGaussianDRM, methods=("stream",))
+    sp2 = make_sparse((9, 10), 40, 2)
+    run("sparse_d2", sp2, (3,), (5,), SparseGaussianDRM, SparseGaussianDRM, methods=("stream",))
+    sp3 = make_sparse((9, 10, 11), 120, 3)
+    run("sparse_d3", sp3, (3, 4), (5, 6), SparseGaussianDRM, TensorTrainDRM, methods=("stream", "orth"))
+    sp5 = make_sparse((5, 6, 7, 8, 4), 400, 4)
+    run("sparse_d5", sp5, (3, 4, 5, 4), (5, 6, 7, 5), SparseGaussianDRM, SparseGaussianDRM, methods=("stream",))
+
+    rng = np.random.default_rng(5)
+    dn = DenseTensor(rng.standard_normal((5, 6, 7, 8)))
+    run("dense", dn, (3, 4, 5), (5, 6, 7), TensorTrainDRM, TensorTrainDRM, methods=("stream", "orth", "hmt"))
+    dn2 = DenseTensor(rng.standard_normal((6, 6, 6)))
+    run("dense_lbig", dn2, (5, 6), (3, 4), TensorTrainDRM, TensorTrainDRM, methods=("stream",))
+
+    tt = TensorTrain.random((7, 8, 9, 10), (4, 5, 3), seed=6)
+    run("tt", tt, (3, 4, 5), (5, 6, 7), TensorTrainDRM, TensorTrainDRM,
+        methods=("stream", "orth", "hmt", "blocked"),
+        lslices=[(0, 0, 0), (1, 2, 2), (3, 4, 5)], rslices=[(0, 0, 0), (2, 3, 4), (5, 6, 7)])
+    cp = CPTensor.random((7, 8, 9, 10), 6, seed=7)
+    run("cp", cp, (3, 4, 5), (5, 6, 7), TensorTrainDRM, TensorTrainDRM, methods=("stream", "orth", "hmt"))
+
+    tsum = TensorSum([tt, sp, cp, 0.5 * TensorTrain.random((7, 8, 9, 10), 2, seed=8)])
+    run("sum", tsum, (3, 4, 5), (5, 6, 7), TensorTrainDRM, TensorTrainDRM,
+        methods=("stream", "orth", "blocked"),
+        lslices=[(0, 0, 0), (2, 2, 2), (3, 4, 5)], rslices=[(0, 0, 0), (4, 4, 4), (5, 6, 7)])
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "sketches.npz"), **store)
+    print("sketches.npz:", names)
+
+
+def gen_ttdrm_cores():
+    """TT-DRM core generation (tensor_train_drm.py:46-56) with the thread count pinned so
+    the fixture is reproducible anywhere: values depend on cpu_count() (App. B-3)."""
+    import multiprocessing
+    store = {"cpu_count": np.int64(multiprocessing.cpu_count())}
+    for name, shape, rank, transpose, seed in [("l", (7, 8, 9, 10), (3, 4, 5), False, 11),
+                                               ("r", (7, 8, 9, 10), (5, 6, 7), True, 23)]:
+        drm = TensorTrainDRM(rank, shape=shape, transpose=transpose, seed=seed)
+        store[name + "_shape"] = np.array(shape)
+        store[name + "_rank"] = np.array(rank)
+        store[name + "_seed"] = np.int64(seed)
+        for i, c in enumerate(drm.cores):
+            store[name + f"_core{i}"] = c
+    np.savez_compressed(os.path.join(OUT, "ttdrm_cores.npz"), **store)
+    print("ttdrm_cores.npz")
+
+
+if __name__ == "__main__":
+    gen_lazy_gaussian()
+    gen_sketches()
+    gen_ttdrm_cores()
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
