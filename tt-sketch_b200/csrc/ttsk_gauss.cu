@@ -1,0 +1,89 @@
+// Stand-alone lazy Gaussian DRM kernels (operator-level entry point + prefix tables).
+// Replaces inds_to_normal, tt_sketch/drm/fast_lazy_gaussian.pyx:183-201.
+#include "ttsk_common.cuh"
+#include "ttsk_gauss.cuh"
+
+namespace ttsk {
+
+struct GaussIdx {
+    const long long* rows[TTSK_MAX_ORDER];
+    long long strides[TTSK_MAX_ORDER];  // int32-wrapped, sign-extended (pyx:60-71)
+    int k;
+};
+
+constexpr int kMaxSalts = 2048;
+
+// one thread per (nonzero p, column a); out is (nnz, rank) row-major so stores coalesce and
+// the k index loads of a warp hit one or two addresses.
+__global__ void __launch_bounds__(256) lazy_gaussian_kernel(GaussIdx gi, long long nnz, int rank_min, int rank,
+                                                           unsigned long long seed, double* __restrict__ out) {
+    __shared__ double2 s_tab[128];
+    __shared__ unsigned long long s_salt[kMaxSalts];
+    load_logtab(s_tab);
+    for (int a = threadIdx.x; a < rank && a < kMaxSalts; a += blockDim.x)
+        s_salt[a] = hash64((unsigned long long)(rank_min + a)) + seed;
+    __syncthreads();
+    const long long total = nnz * (long long)rank;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const long long p = e / rank;
+        const int a = (int)(e - p * rank);
+        unsigned long long flat = 0;
+        if (gi.k > 0) {
+            flat = (unsigned long long)gi.rows[0][p];
+            for (int i = 1; i < gi.k; i++)
+                flat += (unsigned long long)gi.rows[i][p] * (unsigned long long)gi.strides[i];
+        } else {
+            flat = (unsigned long long)p;  // table mode: the flat index IS the row number
+        }
+        const unsigned long long salt =
+            a < kMaxSalts ? s_salt[a] : hash64((unsigned long long)(rank_min + a)) + seed;
+        out[e] = ndtri_any(uniform_from_hash(hash64(flat + salt)), s_tab);
+    }
+}
+
+// strides with the reference's C `int prod` wrap: truncated to 32 bits, sign-extended.
+void wrapped_strides(const int64_t* shape, int k, long long* strides) {
+    int32_t prod = (int32_t)(uint32_t)(uint64_t)shape[0];
+    strides[0] = 1;
+    for (int i = 1; i < k; i++) {
+        strides[i] = (long long)prod;
+        prod = (int32_t)((uint32_t)prod * (uint32_t)(uint64_t)shape[i]);
+    }
+}
+
+int gauss_rows_launch(ttsk_ctx* ctx, const GaussIdx& gi, int64_t nnz, int rank_min, int rank, uint64_t seed,
+                      double* d_out, cudaStream_t st) {
+    if (nnz <= 0 || rank <= 0) return TTSK_OK;
+    const long long total = (long long)nnz * rank;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    lazy_gaussian_kernel<<<(unsigned)blocks, 256, 0, st>>>(gi, nnz, rank_min, rank, seed, d_out);
+    TTSK_LAUNCHED(ctx);
+    return TTSK_OK;
+}
+
+// table of the first `rows` flat indices: out (rows, rank)
+int gauss_table_launch(ttsk_ctx* ctx, int64_t rows, int rank_min, int rank, uint64_t seed, double* d_out,
+                       cudaStream_t st) {
+    GaussIdx gi;
+    gi.k = 0;
+    return gauss_rows_launch(ctx, gi, rows, rank_min, rank, seed, d_out, st);
+}
+
+}  // namespace ttsk
+
+extern "C" int ttsk_lazy_gaussian(ttsk_ctx* ctx, const int64_t* d_idx, int64_t idx_row_stride, int k, int64_t nnz,
+                                  const int64_t* h_shape, int rank_min, int rank_max, uint64_t seed, double* d_out,
+                                  void* stream) {
+    TTSK_ARG(ctx != nullptr, "ctx is NULL");
+    TTSK_ARG(k >= 1 && k <= TTSK_MAX_ORDER, "k out of range");
+    TTSK_ARG(nnz >= 0 && rank_max >= rank_min && rank_min >= 0, "nnz/rank range");
+    TTSK_ARG(h_shape != nullptr && (nnz == 0 || (d_idx && d_out)), "NULL pointer");
+    ttsk::GaussIdx gi;
+    gi.k = k;
+    for (int i = 0; i < k; i++) gi.rows[i] = (const long long*)(d_idx + i * idx_row_stride);
+    ttsk::wrapped_strides(h_shape, k, gi.strides);
+    return ttsk::gauss_rows_launch(ctx, gi, nnz, rank_min, rank_max - rank_min, seed, d_out, (cudaStream_t)stream);
+}

@@ -1,0 +1,246 @@
+// Small dense linear algebra for TT assembly and the orthogonalisation step.
+// Replaces scipy.linalg.lstsq (LAPACK gelsd, SVD based) in tt_sketch/utils.py:98-109 as used by
+// assemble_sketched_tt (tt_sketch/sketch.py:400-443) and orth_step
+// (tt_sketch/sketch_dispatch.py:160-174), and scipy.linalg.qr(mode="economic") there (:172).
+//
+// The matrices are tiny (Omega is at most ~64 x 128; the QR panel is (r*n) x r), so each
+// factorisation runs in ONE thread block out of L2-resident global memory: the work is bound
+// by dependency latency, not by bandwidth or flops.  The pseudo-inverse is formed explicitly
+// (one-sided Jacobi SVD, singular values below rcond*s_max dropped like gelsd) and applied to
+// the (r*n) right-hand sides with ttsk_gemm.
+#include <cfloat>
+
+#include "ttsk_common.cuh"
+
+namespace ttsk {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// W: (rows, c) stored COLUMN-major (W[j*rows + i]); V: (c, c) column-major.
+// One-sided Jacobi with a round-robin tournament: in each round c/2 disjoint column pairs are
+// rotated concurrently, one warp per pair.
+__global__ void __launch_bounds__(1024) jacobi_pinv_kernel(const double* __restrict__ A, int m, int n, double rcond,
+                                                          double* __restrict__ W, double* __restrict__ V,
+                                                          double* __restrict__ sig, double* __restrict__ pinv) {
+    const bool tall = m >= n;
+    const int rows = tall ? m : n, c = tall ? n : m;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    __shared__ int s_rot;
+    __shared__ double s_max;
+    // W = A (tall) or A^T
+    for (int e = tid; e < rows * c; e += blockDim.x) {
+        const int j = e / rows, i = e - j * rows;
+        W[e] = tall ? A[(long long)i * n + j] : A[(long long)j * n + i];
+    }
+    for (int e = tid; e < c * c; e += blockDim.x) V[e] = (e / c == e % c) ? 1.0 : 0.0;
+    __syncthreads();
+    const int cc = (c + 1) & ~1;  // players in the tournament (one dummy if c is odd)
+    for (int sweep = 0; sweep < 60; sweep++) {
+        if (tid == 0) s_rot = 0;
+        __syncthreads();
+        for (int round = 0; round < cc - 1; round++) {
+            for (int k = warp; k < cc / 2; k += nwarps) {
+                // circle method: player cc-1 fixed, others rotate
+                int p = (k == 0) ? cc - 1 : (round + k) % (cc - 1);
+                int q = (round + cc - 1 - k) % (cc - 1);
+                if (p > q) { const int t = p; p = q; q = t; }
+                if (q >= c) continue;  // dummy
+                double* wp = W + (long long)p * rows;
+                double* wq = W + (long long)q * rows;
+                double a = 0.0, b = 0.0, g = 0.0;
+                for (int i = lane; i < rows; i += 32) {
+                    const double x = wp[i], y = wq[i];
+                    a = fma(x, x, a); b = fma(y, y, b); g = fma(x, y, g);
+                }
+                a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
+                if (fabs(g) > 1e-15 * sqrt(a * b) && g != 0.0) {
+                    const double zeta = (b - a) / (2.0 * g);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                    for (int i = lane; i < rows; i += 32) {
+                        const double x = wp[i], y = wq[i];
+                        wp[i] = cs * x - sn * y;
+                        wq[i] = sn * x + cs * y;
+                    }
+                    double* vp = V + (long long)p * c;
+                    double* vq = V + (long long)q * c;
+                    for (int i = lane; i < c; i += 32) {
+                        const double x = vp[i], y = vq[i];
+                        vp[i] = cs * x - sn * y;
+                        vq[i] = sn * x + cs * y;
+                    }
+                    if (lane == 0) s_rot = 1;
+                }
+            }
+            __syncthreads();
+        }
+        const int rot = s_rot;
+        __syncthreads();
+        if (!rot) break;
+    }
+    // singular values = column norms
+    if (tid == 0) s_max = 0.0;
+    __syncthreads();
+    for (int j = warp; j < c; j += nwarps) {
+        double a = 0.0;
+        for (int i = lane; i < rows; i += 32) a = fma(W[(long long)j * rows + i], W[(long long)j * rows + i], a);
+        a = warp_sum(a);
+        if (lane == 0) sig[j] = sqrt(a);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double mx = 0.0;
+        for (int j = 0; j < c; j++) mx = fmax(mx, sig[j]);
+        s_max = mx;
+    }
+    __syncthreads();
+    const double cut = (rcond < 0.0 ? DBL_EPSILON : rcond) * s_max;
+    // pinv (n, m) row-major
+    for (int e = tid; e < n * m; e += blockDim.x) {
+        const int i = e / m, k = e - i * m;  // pinv[i][k]
+        double s = 0.0;
+        for (int j = 0; j < c; j++) {
+            const double sj = sig[j];
+            if (sj > cut) {
+                // tall:  pinv = V S^-2 W^T   -> V[i][j] W[k][j];   wide: pinv = W S^-2 V^T -> W[i][j] V[k][j]
+                const double x = tall ? V[(long long)j * c + i] * W[(long long)j * rows + k]
+                                      : W[(long long)j * rows + i] * V[(long long)j * c + k];
+                s += x / (sj * sj);
+            }
+        }
+        pinv[e] = s;
+    }
+}
+
+// Householder QR of A (m, n) row-major in place, Q (economic) returned in A.  LAPACK dgeqr2 /
+// dorg2r conventions (beta = -sign(alpha) * norm), so Q matches scipy.linalg.qr.
+__global__ void __launch_bounds__(1024) householder_q_kernel(double* __restrict__ A, long long m, int n,
+                                                            double* __restrict__ tau_g) {
+    __shared__ double s_red[32][33];
+    __shared__ double s_w[64];
+    __shared__ double s_scal[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = 0; j < n; j++) {
+        // ---- dlarfg on column j, rows j..m-1
+        double part = 0.0;
+        for (long long i = j + 1 + tid; i < m; i += blockDim.x) {
+            const double x = A[i * n + j];
+            part = fma(x, x, part);
+        }
+        part = warp_sum(part);
+        if (lane == 0) s_red[0][warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double ss = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) ss += s_red[0][w];
+            const double xnorm = sqrt(ss);
+            const double alpha = A[(long long)j * n + j];
+            double tau = 0.0, beta = alpha, scale = 0.0;
+            if (xnorm != 0.0) {
+                beta = -copysign(hypot(alpha, xnorm), alpha);
+                tau = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            s_scal[0] = tau; s_scal[1] = beta; s_scal[2] = scale;
+            tau_g[j] = tau;
+            A[(long long)j * n + j] = beta;
+        }
+        __syncthreads();
+        const double tau = s_scal[0], scale = s_scal[2];
+        if (tau != 0.0) {
+            for (long long i = j + 1 + tid; i < m; i += blockDim.x) A[i * n + j] *= scale;
+            __syncthreads();
+            // ---- apply H_j = I - tau v v^T to columns j+1..n-1 (v_j = 1, v_i = A[i][j])
+            for (int c0 = j + 1; c0 < n; c0 += 32) {
+                const int col = c0 + lane;
+                double w = 0.0;
+                if (col < n)
+                    for (long long i = j + warp; i < m; i += 32) {
+                        const double v = (i == j) ? 1.0 : A[i * n + j];
+                        w = fma(v, A[i * n + col], w);
+                    }
+                s_red[warp][lane] = w;
+                __syncthreads();
+                if (warp == 0) {
+                    double t = 0.0;
+                    for (int r = 0; r < 32; r++) t += s_red[r][lane];
+                    s_w[lane] = t * tau;
+                }
+                __syncthreads();
+                if (col < n) {
+                    const double tw = s_w[lane];
+                    for (long long i = j + warp; i < m; i += 32) {
+                        const double v = (i == j) ? 1.0 : A[i * n + j];
+                        A[i * n + col] -= v * tw;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+    }
+    // ---- dorg2r: Q = H_0 ... H_{n-1} applied to the first n columns of I, built backwards
+    for (int j = n - 1; j >= 0; j--) {
+        const double tau = tau_g[j];
+        // columns j+1..n-1 of Q (already formed for rows >= j+1; row j of them is 0) get H_j applied
+        for (int c0 = j + 1; c0 < n; c0 += 32) {
+            const int col = c0 + lane;
+            double w = 0.0;
+            if (col < n)
+                for (long long i = j + 1 + warp; i < m; i += 32) w = fma(A[i * n + j], A[i * n + col], w);
+            s_red[warp][lane] = w;
+            __syncthreads();
+            if (warp == 0) {
+                double t = 0.0;
+                for (int r = 0; r < 32; r++) t += s_red[r][lane];
+                s_w[lane] = t * tau;
+            }
+            __syncthreads();
+            if (col < n) {
+                const double tw = s_w[lane];
+                if (warp == 0) A[(long long)j * n + col] = -tw;  // row j: 0 - 1*tw
+                for (long long i = j + 1 + warp; i < m; i += 32) A[i * n + col] -= A[i * n + j] * tw;
+            }
+            __syncthreads();
+        }
+        // column j itself: Q[:, j] = e_j - tau v
+        for (long long i = j + 1 + tid; i < m; i += blockDim.x) A[i * n + j] *= -tau;
+        if (tid == 0) A[(long long)j * n + j] = 1.0 - tau;
+        for (int r = tid; r < j; r += blockDim.x) A[(long long)r * n + j] = 0.0;
+        __syncthreads();
+    }
+}
+
+}  // namespace ttsk
+
+extern "C" int ttsk_pinv(ttsk_ctx* ctx, const double* d_A, int m, int n, double rcond, double* d_pinv, void* stream) {
+    TTSK_ARG(ctx != nullptr, "ctx is NULL");
+    TTSK_ARG(m >= 1 && n >= 1 && m <= 4096 && n <= 4096 && (m <= 256 || n <= 256), "pinv: min(m, n) must be <= 256");
+    TTSK_ARG(d_A && d_pinv, "NULL pointer");
+    const int rows = m >= n ? m : n, c = m >= n ? n : m;
+    const int64_t need = ((int64_t)rows * c + (int64_t)c * c + c) * 8 + 1024;
+    TTSK_TRY(ctx->ws_reserve(need));
+    ctx->ws_reset();
+    double* W = (double*)ctx->ws_alloc((int64_t)rows * c * 8);
+    double* V = (double*)ctx->ws_alloc((int64_t)c * c * 8);
+    double* sig = (double*)ctx->ws_alloc((int64_t)c * 8);
+    ttsk::jacobi_pinv_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_A, m, n, rcond, W, V, sig, d_pinv);
+    TTSK_LAUNCHED(ctx);
+    return TTSK_OK;
+}
+
+extern "C" int ttsk_qr_q(ttsk_ctx* ctx, double* d_A, int64_t m, int n, void* stream) {
+    TTSK_ARG(ctx != nullptr, "ctx is NULL");
+    TTSK_ARG(m >= n && n >= 1 && n <= 1024, "qr: need m >= n >= 1");
+    TTSK_ARG(d_A != nullptr, "NULL pointer");
+    TTSK_TRY(ctx->ws_reserve((int64_t)n * 8 + 1024));
+    ctx->ws_reset();
+    double* tau = (double*)ctx->ws_alloc((int64_t)n * 8);
+    ttsk::householder_q_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_A, m, n, tau);
+    TTSK_LAUNCHED(ctx);
+    return TTSK_OK;
+}

@@ -1,0 +1,116 @@
+"""Random tensor-train DRM: sketches by partial contractions with a fixed Gaussian TT.
+
+Mirror of tt_sketch/drm/tensor_train_drm.py:23-122 (reference): same constructor, same core
+values (cores come from TensorTrain.random(..., norm_goal="norm-preserve") on the HOST, because
+the reference's generator depends on the host's cpu_count(); they are uploaded once), same
+`sketch_sparse / sketch_tt / sketch_cp / sketch_dense` generators.  Every contraction is a
+libttsk kernel: strided FP64 GEMMs for TT / CP / dense input, the per-nonzero chain kernel for
+sparse input.  `sketch_tucker` is out of scope.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Union
+
+import numpy as np
+
+from tt_sketch import _backend as be
+from tt_sketch.drm_base import CanSlice, handle_transpose
+from tt_sketch.sketching_methods.abstract_methods import (CansketchCP, CansketchDense, CansketchSparse,
+                                                          CansketchTT)
+from tt_sketch.tensor import CPTensor, DenseTensor, SparseTensor, TensorTrain
+
+
+class TensorTrainDRM(CansketchSparse, CansketchTT, CansketchCP, CanSlice, CansketchDense):
+    kind = be.DRM_TT
+
+    def __init__(self, rank: Union[Tuple[int, ...], int], shape: Tuple[int, ...], transpose: bool,
+                 seed: Optional[int] = None, **kwargs) -> None:
+        super().__init__(rank, shape, transpose, seed=seed, **kwargs)
+        if "cores" in kwargs:
+            self.cores = kwargs["cores"]
+        else:
+            tt_shape = self.shape[::-1] if transpose else self.shape
+            tt = TensorTrain.random(tt_shape, self.true_rank, self.seed, norm_goal="norm-preserve")
+            self.cores = tt.cores[:-1]
+        self._dev_cores = kwargs.get("_dev_cores", {})
+
+    def _slice_kwargs(self):
+        # a slice shares the parent's cores (the reference regenerates identical ones)
+        return {"cores": self.cores, "_dev_cores": self._dev_cores}
+
+    def device_core(self, k: int):
+        """Core k (DRM orientation) as a contiguous device tensor, uploaded once."""
+        c = self.cores[k]
+        if be.is_device(c):
+            return c if c.is_contiguous() else c.contiguous()
+        key = id(c)
+        if key not in self._dev_cores:
+            self._dev_cores[key] = be.to_device(c, np.float64)
+        return self._dev_cores[key]
+
+    # ------------------------------------------------------------------ sparse
+    @handle_transpose
+    def sketch_sparse_device(self, tensor: SparseTensor):
+        """Chained per-nonzero core products v_mu = v_{mu-1} @ core_mu[:, i_mu, :]; yields the
+        column slice [rank_min, rank_max) as a (rank, nnz) view."""
+        idx = tensor.device()["indices"]
+        v, mu = None, 0
+        while mu < len(self.cores):  # re-read every step: OrthogTTDRM appends cores lazily
+            v = be.ttdrm_sparse_step(idx[mu], v, self.device_core(mu))
+            yield v[:, self.rank_min[mu]:self.rank_max[mu]].T
+            mu += 1
+
+    # ------------------------------------------------------------------ tensor train
+    @handle_transpose
+    def sketch_tt_device(self, tensor: TensorTrain):
+        """lr_mu (r_T, r_D): DRM contracted with the first mu+1 cores of the TT."""
+        cores = tensor.device()["cores"]
+        lr, mu = None, 0
+        while mu < len(self.cores):
+            c, g = cores[mu], self.device_core(mu)
+            rT0, n, rT1 = c.shape
+            rD0, _, rD1 = g.shape
+            if mu == 0:
+                lr = be.gemm(c.reshape(n, rT1).T, g.reshape(n, rD1))
+            else:
+                w = be.gemm(lr.T, c.reshape(rT0, n * rT1))            # (rD0, n*rT1)
+                lr = be.gemm(w.reshape(rD0 * n, rT1).T, g.reshape(rD0 * n, rD1))
+            yield lr[:, self.rank_min[mu]:self.rank_max[mu]]
+            mu += 1
+
+    # ------------------------------------------------------------------ CP
+    @handle_transpose
+    def sketch_cp_device(self, tensor: CPTensor):
+        """lr_mu (R_cp, r_D):  lr_mu[i, l] = sum_{j,k} lr_{mu-1}[i, j] A_mu[k, i] G_mu[j, k, l]."""
+        cores = tensor.device()["cores"]
+        lr, mu = None, 0
+        while mu < len(self.cores):
+            a, g = cores[mu], self.device_core(mu)
+            n, R = a.shape
+            rD0, _, rD1 = g.shape
+            if mu == 0:
+                lr = be.gemm(a.T, g.reshape(n, rD1))
+            else:
+                w = be.gemm(lr, g.reshape(rD0, n * rD1)).reshape(R, n, rD1)   # w[i, k, l]
+                out = be.empty((R, 1, rD1))
+                # batched over the CP index i: (1 x n) row A[:, i] times (n x rD1) slab w[i]
+                be.gemm_batched(a.T.unsqueeze(1), w, out)
+                lr = out.reshape(R, rD1)
+            yield lr[:, self.rank_min[mu]:self.rank_max[mu]]
+            mu += 1
+
+    # ------------------------------------------------------------------ dense
+    @handle_transpose
+    def sketch_dense_device(self, tensor: DenseTensor):
+        """Dense unfoldings of the DRM itself, (true_rank[mu], prod(shape[:mu+1])); like the
+        reference this ignores rank_min/rank_max (no blocked dense sketch)."""
+        g0 = self.device_core(0)
+        pc = g0.reshape(-1, g0.shape[-1])
+        yield pc.T
+        mu = 1
+        while mu < len(self.cores):
+            g = self.device_core(mu)
+            r0, n, r1 = g.shape
+            pc = be.gemm(pc, g.reshape(r0, n * r1)).reshape(-1, r1)
+            yield pc.T
+            mu += 1

@@ -1,0 +1,301 @@
+"""Driver of the sketching path: picks the DRM contraction and the Omega/Psi kernels for a
+tensor type and runs the streaming / orthogonal / HMT loops on the GPU.
+
+Mirror of tt_sketch/sketch_dispatch.py (reference): registries DRM_SKETCH_METHOD_DISPATCH /
+OMEGA_METHODS / PSI_METHODS (:59-82), TensorSum handling (:85-147), get_sketch_method (:150-157),
+orth_step (:160-174), OrthogTTDRM (:177-193), SketchMethod (:196-199), general_sketch (:202-275).
+
+Execution model (B200): the whole sketch lives in ONE packed device buffer
+[Psi_0|...|Psi_{d-1}|Omega_0|...|Omega_{d-2}]; every summand of a TensorSum accumulates into it
+(the sketch is linear), and it is copied to the host once at the end (or all-reduced across
+GPUs first, see tt_sketch/distributed.py).  Sparse summands of a streaming sketch go through the
+fused `ttsk_sparse_sketch` entry point (DRM entries generated on the fly, nothing
+materialised); everything else runs the per-bond device operators registered below.
+"""
+from __future__ import annotations
+
+import enum
+from ctypes import byref
+from functools import partial
+from typing import Callable, List, Optional
+
+import numpy as np
+
+from tt_sketch import _backend as be
+from tt_sketch.drm import SparseGaussianDRM, TensorTrainDRM
+from tt_sketch.drm_base import DRM
+from tt_sketch.sketch_container import SketchContainer
+from tt_sketch.sketching_methods.abstract_methods import (CansketchCP, CansketchDense, CansketchSparse,
+                                                          CansketchTT)
+from tt_sketch.sketching_methods.cp_sketch import (omega_cp_device, psi_cp_device, sketch_omega_cp,
+                                                   sketch_psi_cp)
+from tt_sketch.sketching_methods.dense_sketch import (omega_dense_device, psi_dense_device,
+                                                      sketch_omega_dense, sketch_psi_dense)
+from tt_sketch.sketching_methods.sparse_sketch import (omega_sparse_device, psi_sparse_device,
+                                                       sketch_omega_sparse, sketch_psi_sparse)
+from tt_sketch.sketching_methods.tensor_train_sketch import (omega_tt_device, psi_tt_device,
+                                                             sketch_omega_tt, sketch_psi_tt)
+from tt_sketch.tensor import CPTensor, DenseTensor, SparseTensor, Tensor, TensorSum, TensorTrain
+from tt_sketch.utils import right_mul_pinv  # noqa: F401  (re-exported like the reference)
+
+ABSTRACT_TENSOR_SKETCH_DISPATCH = {
+    SparseTensor: CansketchSparse,
+    TensorTrain: CansketchTT,
+    DenseTensor: CansketchDense,
+    CPTensor: CansketchCP,
+}
+
+# tensor class -> name of the DRM method that contracts the DRM with it (host arrays)
+DRM_SKETCH_METHOD_DISPATCH = {
+    SparseTensor: "sketch_sparse",
+    TensorTrain: "sketch_tt",
+    DenseTensor: "sketch_dense",
+    CPTensor: "sketch_cp",
+}
+
+# the plug-in point: NumPy-in / NumPy-out operators, mutable like the reference's dicts
+OMEGA_METHODS = {
+    SparseTensor: sketch_omega_sparse,
+    TensorTrain: sketch_omega_tt,
+    DenseTensor: sketch_omega_dense,
+    CPTensor: sketch_omega_cp,
+}
+PSI_METHODS = {
+    SparseTensor: sketch_psi_sparse,
+    TensorTrain: sketch_psi_tt,
+    DenseTensor: sketch_psi_dense,
+    CPTensor: sketch_psi_cp,
+}
+
+# device-resident twins used by general_sketch (accumulate into `out`)
+OMEGA_DEVICE = {
+    SparseTensor: omega_sparse_device,
+    TensorTrain: omega_tt_device,
+    DenseTensor: omega_dense_device,
+    CPTensor: omega_cp_device,
+}
+PSI_DEVICE = {
+    SparseTensor: psi_sparse_device,
+    TensorTrain: psi_tt_device,
+    DenseTensor: psi_dense_device,
+    CPTensor: psi_cp_device,
+}
+
+
+# ------------------------------------------------------------------ TensorSum (host-level API)
+def sketch_omega_sum(left_sketch_array, right_sketch_array, *, tensor: TensorSum, omega_shape, **kwargs):
+    total = np.zeros(omega_shape)
+    for X, L, R in zip(tensor.tensors, left_sketch_array, right_sketch_array):
+        total += OMEGA_METHODS[type(X)](L, R, tensor=X, omega_shape=omega_shape, **kwargs)
+    return total
+
+
+def sketch_psi_sum(left_sketch_array, right_sketch_array, *, tensor: TensorSum, psi_shape, **kwargs):
+    n = tensor.num_summands
+    Ls = left_sketch_array if left_sketch_array is not None else (None,) * n
+    Rs = right_sketch_array if right_sketch_array is not None else (None,) * n
+    total = np.zeros(psi_shape)
+    for X, L, R in zip(tensor.tensors, Ls, Rs):
+        total += PSI_METHODS[type(X)](L, R, tensor=X, psi_shape=psi_shape, **kwargs)
+    return total
+
+
+OMEGA_METHODS[TensorSum] = sketch_omega_sum
+PSI_METHODS[TensorSum] = sketch_psi_sum
+
+
+def sum_sketch(tensor: TensorSum, *, drm: DRM):
+    """Per-summand DRM contractions advanced in lock step: yields one tuple per bond."""
+    gens = [get_sketch_method(X, drm)(X) for X in tensor.tensors]
+    for _ in range(len(tensor.shape) - 1):
+        yield tuple(next(g) for g in gens)
+
+
+def get_sketch_method(tensor: Tensor, drm: DRM, device: bool = False) -> Callable:
+    name = DRM_SKETCH_METHOD_DISPATCH.get(type(tensor))
+    if name is not None:
+        return getattr(drm, name + "_device" if device else name)
+    if isinstance(tensor, TensorSum):
+        return partial(sum_sketch, drm=drm)
+    raise ValueError(f"DRM of type {type(drm)} can't sketch {type(tensor)}")
+
+
+# ------------------------------------------------------------------ orthogonalisation step
+def orth_step_device(Psi, Omega):
+    """Psi (r1, n, rR) device, Omega (rL, rR) device or None -> Q factor reshaped (r1, n, rL|rR).
+    Psi_mat @ pinv(Omega) by Jacobi-SVD pseudo-inverse + GEMM, then Householder QR."""
+    r1, n, r2 = Psi.shape
+    mat = Psi.reshape(r1 * n, r2)
+    if Omega is not None:
+        mat = be.gemm(mat, be.pinv(Omega))
+    else:
+        mat = mat.clone()
+    if mat.shape[0] < mat.shape[1]:
+        raise ValueError(f"cannot orthogonalise a {tuple(mat.shape)} unfolding: rank exceeds r*n (trim the rank)")
+    be.qr_q_inplace(mat)
+    return mat.reshape(r1, n, mat.shape[1])
+
+
+def orth_step(Psi: np.ndarray, Omega: Optional[np.ndarray]) -> np.ndarray:
+    """NumPy-level twin of the reference's orth_step (sketch_dispatch.py:160-174)."""
+    q = orth_step_device(be.to_device(Psi, np.float64), be.to_device(Omega, np.float64) if Omega is not None else None)
+    return be.to_host(q)
+
+
+class OrthogTTDRM:
+    """Left DRM of the orthogonal / HMT loops: a TensorTrainDRM whose cores are the
+    orthogonalised Psi cores produced so far (device tensors), contracted lazily."""
+
+    def __init__(self, rank, tensor):
+        self.rank = rank
+        self.drm = TensorTrainDRM(rank, tensor.shape, transpose=False, cores=[])
+        self.tensor = tensor
+        self.generators = None
+
+    def add_core(self, core):
+        self.drm.cores.append(core)
+        if self.generators is None:
+            self.generators = [get_sketch_method(X, self.drm, device=True)(X) for X in _summands(self.tensor)]
+
+    def __next__(self):
+        return [next(g) for g in self.generators]
+
+
+class SketchMethod(enum.Enum):
+    streaming = "streaming"
+    orthogonal = "orthogonal"
+    hmt = "hmt"
+
+
+def _summands(tensor: Tensor) -> List[Tensor]:
+    if isinstance(tensor, TensorSum):
+        out: List[Tensor] = []
+        for X in tensor.tensors:
+            out.extend(_summands(X))
+        return out
+    return [tensor]
+
+
+def _check_supported(X: Tensor, drm: DRM):
+    if type(X) not in DRM_SKETCH_METHOD_DISPATCH:
+        raise ValueError(f"DRM of type {type(drm)} can't sketch {type(X)}")
+    name = DRM_SKETCH_METHOD_DISPATCH[type(X)] + "_device"
+    getattr(drm, name)  # AttributeError if the DRM lacks the capability (like the reference)
+
+
+def drm_descriptor(drm: DRM):
+    """ctypes `ttsk_drm` for a SparseGaussianDRM / TensorTrainDRM (plus keep-alive refs)."""
+    desc = be.TtskDrm()
+    desc.kind = drm.kind
+    desc.right = 1 if drm.transpose else 0
+    desc.seed = int(drm.seed)
+    keep = []
+    for mu, (lo, hi) in enumerate(zip(drm.bond_rank_min, drm.bond_rank_max)):
+        desc.rank_min[mu], desc.rank_max[mu] = int(lo), int(hi)
+    if drm.kind == be.DRM_TT:
+        for k in range(len(drm.cores)):
+            c = drm.device_core(k)
+            keep.append(c)
+            desc.d_cores[k] = c.data_ptr()
+            desc.core_r0[k], desc.core_r1[k] = int(c.shape[0]), int(c.shape[2])
+    return desc, keep
+
+
+def _fused_sparse(X: SparseTensor, left_drm: DRM, right_drm: DRM, packed, accumulate: bool):
+    dev = X.device()
+    idx, val = dev["indices"], dev["entries"]
+    ld, lkeep = drm_descriptor(left_drm)
+    rd, rkeep = drm_descriptor(right_drm)
+    be.check(be.lib().ttsk_sparse_sketch(be.ctx(), X.ndim, be.as_i64(X.shape), X.nnz, be.ptr(idx), idx.stride(0),
+                                         be.ptr(val), byref(ld), byref(rd), be.ptr(packed),
+                                         1 if accumulate else 0, be.stream()))
+    del lkeep, rkeep
+
+
+def _fusable(X: Tensor, left_drm: DRM, right_drm: DRM) -> bool:
+    return (isinstance(X, SparseTensor) and type(left_drm) in (SparseGaussianDRM, TensorTrainDRM)
+            and type(right_drm) in (SparseGaussianDRM, TensorTrainDRM)
+            and max(max(left_drm.rank), max(right_drm.rank)) <= 64 and X.nnz > 0)
+
+
+def streaming_sketch_device(tensor: Tensor, left_drm: DRM, right_drm: DRM, packed=None):
+    """Accumulate the streaming sketch of `tensor` into the packed device buffer (allocated and
+    zeroed if None) and return it with its layout.  Used by general_sketch and by the multi-GPU
+    driver, which all-reduces the buffer before it is unpacked."""
+    shape = tuple(tensor.shape)
+    d = len(shape)
+    rL, rR = tuple(left_drm.bond_rank), tuple(right_drm.bond_rank)
+    items, total = SketchContainer.layout(shape, rL, rR)
+    if packed is None:
+        packed = be.zeros(total)
+    views = [packed[o:o + int(np.prod(s))].reshape(s) for o, s in items]
+    for X in _summands(tensor):
+        if tuple(X.shape) != shape:
+            raise ValueError(f"Shape {left_drm.shape} of DRM doesn't match tensor's shape {X.shape}")
+        if _fusable(X, left_drm, right_drm):
+            if tuple(left_drm.shape) != shape or tuple(right_drm.shape) != shape:
+                raise ValueError(f"Shape {left_drm.shape} of DRM doesn't match tensor's shape {shape}")
+            _fused_sparse(X, left_drm, right_drm, packed, accumulate=True)
+            continue
+        _check_supported(X, left_drm)
+        _check_supported(X, right_drm)
+        Lc = list(get_sketch_method(X, left_drm, device=True)(X))
+        Rc = list(get_sketch_method(X, right_drm, device=True)(X))
+        om, ps = OMEGA_DEVICE[type(X)], PSI_DEVICE[type(X)]
+        for mu in range(d - 1):
+            om(Lc[mu], Rc[mu], tensor=X, mu=mu, out=views[d + mu])
+        for mu in range(d):
+            ps(Lc[mu - 1] if mu > 0 else None, Rc[mu] if mu < d - 1 else None, tensor=X, mu=mu, out=views[mu])
+    return packed, (shape, rL, rR)
+
+
+def _sequential_sketch(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, method: SketchMethod):
+    """orthogonal / HMT: Psi_mu depends on the QR of Psi_{mu-1}, so bonds are processed in order;
+    all intermediates stay on the device."""
+    shape = tuple(tensor.shape)
+    d = len(shape)
+    parts = _summands(tensor)
+    rR = tuple(right_drm.bond_rank)
+    for X in parts:
+        _check_supported(X, right_drm)
+    Rc = [list(get_sketch_method(X, right_drm, device=True)(X)) for X in parts]
+    Omega = []
+    if method == SketchMethod.orthogonal:
+        rL = tuple(left_drm.bond_rank)
+        for X in parts:
+            _check_supported(X, left_drm)
+        Lc = [list(get_sketch_method(X, left_drm, device=True)(X)) for X in parts]
+        for mu in range(d - 1):
+            o = be.zeros((rL[mu], rR[mu]))
+            for s, X in enumerate(parts):
+                OMEGA_DEVICE[type(X)](Lc[s][mu], Rc[s][mu], tensor=X, mu=mu, out=o)
+            Omega.append(o)
+        del Lc
+    else:
+        rL = rR  # HMT: the left rank is only needed for shapes (reference :220-222)
+    left_psi = OrthogTTDRM(rL, tensor)
+    Psi = []
+    for mu in range(d):
+        r1 = rL[mu - 1] if mu > 0 else 1
+        r2 = rR[mu] if mu < d - 1 else 1
+        lefts = [None] * len(parts)
+        if mu > 0:
+            left_psi.add_core(Psi[-1])
+            lefts = next(left_psi)
+        P = be.zeros((r1, shape[mu], r2))
+        for s, X in enumerate(parts):
+            PSI_DEVICE[type(X)](lefts[s], Rc[s][mu] if mu < d - 1 else None, tensor=X, mu=mu, out=P)
+        if mu < d - 1:
+            P = orth_step_device(P, Omega[mu] if method == SketchMethod.orthogonal else None)
+        Psi.append(P)
+    return SketchContainer([be.to_host(p) for p in Psi], [be.to_host(o) for o in Omega])
+
+
+def general_sketch(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, method: SketchMethod) -> SketchContainer:
+    """Sketch `tensor` with the given DRMs; returns host arrays in a SketchContainer."""
+    if method != SketchMethod.hmt and left_drm is None:
+        raise ValueError(f"left_drm must be provided for method '{method}'")
+    if method == SketchMethod.streaming:
+        packed, (shape, rL, rR) = streaming_sketch_device(tensor, left_drm, right_drm)
+        return SketchContainer.unpack(be.to_host(packed), shape, rL, rR)
+    return _sequential_sketch(tensor, left_drm, right_drm, method)
