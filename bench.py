@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- stream_sketch throughput of the B200 sketching path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--nnz NNZ] [--impl reference]
+
+Workload (BASELINE.json configs[3], SURVEY.md section 8d "C4"): one step = one streaming sketch
+(all d Psi cores + d-1 Omega matrices) of a synthetic order-4 COO tensor, shape
+(10^4, 10^4, 10^4, 500), nnz = 1e8 (uniform int64 indices, N(0,1) float64 values), with lazy
+SparseGaussianDRMs, left rank 20 (seed 1) / right rank 40 (seed 2).  `value` = nonzeros per
+second with the COO arrays resident in HBM; `e2e` = the same through the host-buffer C-ABI call
+(pinned host COO -> chunked H2D overlapped with the kernels -> packed sketch D2H).
+Multi-GPU (torchrun, one rank per GPU): the SAME 1e8 nonzeros are sharded into equal contiguous
+ranges (strong scaling), every rank sketches its shard, one NCCL all-reduce of the packed
+sketch (16.4 M doubles) combines them inside the timed region.
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, incl. its
+O(n_mu * nnz) mask loop) on a bounded sample of the same workload on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tt-sketch_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SHAPE = (10000, 10000, 10000, 500)
+RL, RR = (20, 20, 20), (40, 40, 40)
+SEED_L, SEED_R = 1, 2
+METRIC = "stream_sketch nnz/sec (sparse)"
+UNIT = "nnz/s"
+ALGO_BYTES_PER_NNZ = 8 * (len(SHAPE) + 1)  # int64 COO indices + fp64 value, read once
+
+
+def make_coo(nnz, lo, hi):
+    """Nonzeros [lo, hi) of the synthetic tensor: generated blockwise from per-block seeds so
+    every rank can build exactly its shard of the same global tensor."""
+    blk = 1 << 22
+    idx = np.empty((len(SHAPE), hi - lo), dtype=np.int64)
+    val = np.empty(hi - lo, dtype=np.float64)
+    b0 = lo // blk
+    pos = 0
+    b = b0
+    while pos < hi - lo:
+        start = max(lo, b * blk)
+        stop = min(hi, (b + 1) * blk)
+        n_blk = min(blk, nnz - b * blk)
+        rng = np.random.default_rng([1234, b])
+        full_idx = [rng.integers(0, n, n_blk) for n in SHAPE]
+        full_val = rng.standard_normal(n_blk)
+        s0, s1 = start - b * blk, stop - b * blk
+        for k in range(len(SHAPE)):
+            idx[k, pos:pos + (s1 - s0)] = full_idx[k][s0:s1]
+        val[pos:pos + (s1 - s0)] = full_val[s0:s1]
+        pos += s1 - s0
+        b += 1
+    return idx, val
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(nnz_sample, repeats=1):
+    """The reference algorithm (oracle port: hash->ndtri rows materialised per bond, Omega GEMM,
+    Psi by the O(n_mu*nnz) boolean-mask loop of sparse_sketch.py:49-69) on the host."""
+    from oracle import sketch_oracle as orc
+
+    idx, val = make_coo(nnz_sample, 0, nnz_sample)
+    oL = orc.Drm("gauss", False, SHAPE, (0,) * 3, RL, SEED_L)
+    oR = orc.Drm("gauss", True, SHAPE, (0,) * 3, RR, SEED_R)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.general_sketch(("sparse", SHAPE, idx, val), oL, oR, "streaming")
+        best = min(best, time.perf_counter() - t0)
+    return nnz_sample / best, best
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    sample = args.ref_nnz
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, sec = cpu_reference_rate(sample)
+        if i >= args.warmup:
+            times.append(sec)
+    sec = float(np.mean(times))
+    value = sample / sec
+    cores = blas_threads()
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.nnz, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"first {sample} nonzeros of the workload per step (the reference cannot run "
+                                   f"nnz=1e8: >=144 GB of (r x nnz) intermediates, ~5.7 h); NumPy oracle port of the "
+                                   f"reference algorithm incl. its O(n_mu*nnz) mask loop; BLAS threads={cores}, the "
+                                   f"generator and mask loop are single-threaded like the reference"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def config_dict(nnz, gpus):
+    return {"workload": "C4: stream_sketch of sparse order-4 COO tensor, shape (1e4,1e4,1e4,500), "
+                        f"nnz={nnz:.3g}, SparseGaussianDRM lazy DRMs, left rank 20 / right rank 40, float64",
+            "nnz": int(nnz), "shape": list(SHAPE), "left_rank": list(RL), "right_rank": list(RR),
+            "sharding": f"nnz split into {gpus} equal contiguous ranges, one NCCL all-reduce of the packed sketch",
+            "l2": "inputs (4.0 GB COO) are larger than the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--nnz", type=float, default=1e8)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--ref-nnz", type=int, default=20000, help="sample size of one --impl reference step")
+    ap.add_argument("--cpu-nnz", type=int, default=50000, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.nnz = int(args.nnz)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from ctypes import byref, c_double
+
+    from tt_sketch import _backend as be
+    from tt_sketch.drm import SparseGaussianDRM
+    from tt_sketch.sketch_container import SketchContainer
+    from tt_sketch.sketch_dispatch import drm_descriptor
+
+    nnz = args.nnz
+    lo, hi = rank * nnz // world, (rank + 1) * nnz // world
+    n_loc = hi - lo
+    t0 = time.perf_counter()
+    idx, val = make_coo(nnz, lo, hi)
+    gen_s = time.perf_counter() - t0
+    left = SparseGaussianDRM(RL, shape=SHAPE, transpose=False, seed=SEED_L)
+    right = SparseGaussianDRM(RR, shape=SHAPE, transpose=True, seed=SEED_R)
+    ld, _ = drm_descriptor(left)
+    rd, _ = drm_descriptor(right)
+    _, total = SketchContainer.layout(SHAPE, RL, RR)
+    lib, ctx = be.lib(), be.ctx()
+    shape_c = be.as_i64(SHAPE)
+
+    # ---------------- device-resident arm (`value`)
+    d_idx = torch.from_numpy(idx).cuda()
+    d_val = torch.from_numpy(val).cuda()
+    packed = torch.empty(total, dtype=torch.float64, device="cuda")
+
+    def step_device():
+        be.check(lib.ttsk_sparse_sketch(ctx, len(SHAPE), shape_c, n_loc, be.ptr(d_idx), d_idx.stride(0), be.ptr(d_val),
+                                        byref(ld), byref(rd), be.ptr(packed), 0, be.stream()))
+        if world > 1:
+            dist.all_reduce(packed)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = be.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pass_ms, total_ms = [], []
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = be.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # per-kernel timing of the dominant kernel (events recorded by the library on the same stream
+    # around every pass launch of the LAST timed step)
+    a, b = c_double(), c_double()
+    be.check(lib.ttsk_last_kernel_ms(ctx, byref(a), byref(b)))
+    step_kernels_ms, pass_kernels_ms = a.value, b.value
+    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, launches = float(tmax[0]), int(tsum[1])
+    ms_per_step = ms / args.steps
+    value = nnz / (ms_per_step * 1e-3)
+    checksum = float(packed.sum().item())
+
+    # ---------------- end-to-end arm (host COO buffers through the C ABI)
+    e2e = None
+    if not args.no_e2e:
+        h_idx = torch.from_numpy(idx).pin_memory()
+        h_val = torch.from_numpy(val).pin_memory()
+        h_out = torch.empty(total, dtype=torch.float64).pin_memory()
+
+        def step_e2e():
+            if world == 1:
+                be.check(lib.ttsk_sparse_sketch_host(ctx, len(SHAPE), shape_c, n_loc, h_idx.data_ptr(), h_idx.stride(0),
+                                                     h_val.data_ptr(), byref(ld), byref(rd), h_out.data_ptr(), 0))
+            else:
+                be.check(lib.ttsk_sparse_sketch_stream(ctx, len(SHAPE), shape_c, n_loc, h_idx.data_ptr(),
+                                                       h_idx.stride(0), h_val.data_ptr(), byref(ld), byref(rd),
+                                                       be.ptr(packed), 0))
+                dist.all_reduce(packed)
+                h_out.copy_(packed, non_blocking=True)
+                torch.cuda.synchronize()
+
+        step_e2e()
+        sync_all()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e):
+            step_e2e()
+        sync_all()
+        e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        te = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te[0])
+        e2e = {"value": nnz / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(n_loc * ALGO_BYTES_PER_NNZ), "d2h_bytes_per_step": int(total * 8),
+               "api": "ttsk_sparse_sketch_host (C ABI, pinned host COO in, packed sketch out)"
+               if world == 1 else "ttsk_sparse_sketch_stream + NCCL all-reduce + D2H",
+               "checksum_matches_device_arm": bool(abs(float(h_out.sum()) - (checksum if world == 1 else float(packed.sum().item())))
+                                                   <= 1e-6 * max(1.0, abs(checksum)))}
+
+    if rank == 0:
+        peak, which = measured_hbm_peak()
+        n_pass = len(SHAPE)
+        achieved = ALGO_BYTES_PER_NNZ * n_loc / (pass_kernels_ms * 1e-3) / 1e9 if pass_kernels_ms > 0 else 0.0
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(nnz, world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": which, "kernel": "ttsk::sparse_pass_kernel",
+                         "launches_per_step": n_pass,
+                         "note": "algorithmic 40 B/nnz over the d=4 mode passes (10 B/nnz per launch) / summed pass "
+                                 "time of the last step; the kernel is FP64-issue-bound (bit-exact ndtri), see "
+                                 "fp64_pipe and DESIGN.md section 5"},
+            "fp64_pipe": fp64_model(n_loc, pass_kernels_ms),
+            "kernel_ms": {"pass_kernels_last_step": pass_kernels_ms, "all_kernels_last_step": step_kernels_ms},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "host": {"coo_generation_s": gen_s, "cpu_count": os.cpu_count()},
+            "checksum": checksum,
+        }
+        if world == 1 and not args.no_cpu:
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+            rate, sec = cpu_reference_rate(args.cpu_nnz)
+            cores = blas_threads()
+            out["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"first {args.cpu_nnz} nonzeros of the same workload, one run of {sec:.1f} s; NumPy oracle port "
+                          f"of the reference algorithm (mask loop O(n_mu*nnz)); BLAS threads={cores}, generator and "
+                          f"mask loop single-threaded like the reference"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def fp64_model(n_loc, pass_ms):
+    """FP64-pipe view of the same kernel: FP64 instructions the algorithm needs per nonzero
+     over the measured DFMA issue rate of this B200 (tools/fp64_microbench)."""
+    otf_variates = 20 + 20 + 40            # L_1, L_2, R_0 (L_0, R_1, R_2 come from prefix tables)
+    per_variate = 0.73 * 42 + 0.27 * 112   # central / tail branch FP64 instructions
+    mma_fma = 8 * 40 + 2 * 24 * 40 + 24 * 40 + 24 * 8  # Psi_0, Psi_1+Psi_2, Omega_1, Psi_3 (8x8x4 padded tiles)
+    per_nnz = otf_variates * per_variate + mma_fma
+    peak = 1.68e13
+    ach = per_nnz * n_loc / (pass_ms * 1e-3) if pass_ms > 0 else 0.0
+    return {"fp64_instr_per_nnz_model": per_nnz, "achieved_instr_per_s": ach, "peak_instr_per_s": peak,
+            "frac": ach / peak, "peak_source": "measured DFMA issue rate, tools/fp64_microbench on this pool's B200"}
+
+
+if __name__ == "__main__":
+    main()

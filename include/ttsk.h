@@ -114,6 +114,12 @@ int ttsk_sparse_sketch_host(ttsk_ctx *ctx, int d, const int64_t *h_shape, int64_
                             const int64_t *h_idx, int64_t idx_row_stride, const double *h_val,
                             const ttsk_drm *left, const ttsk_drm *right, double *h_out,
                             int accumulate);
+/* Host COO buffers in, DEVICE packed sketch out (so partial sketches of several GPUs can be
+ * all-reduced before one device->host copy).  Synchronous; runs on the context's own streams. */
+int ttsk_sparse_sketch_stream(ttsk_ctx *ctx, int d, const int64_t *h_shape, int64_t nnz,
+                              const int64_t *h_idx, int64_t idx_row_stride, const double *h_val,
+                              const ttsk_drm *left, const ttsk_drm *right, double *d_out,
+                              int accumulate);
 
 /* Operator-level sparse kernels on explicit per-nonzero DRM rows (the reference's per-mu
  * plug-in signatures).  Element (nonzero p, column a) of the left rows is

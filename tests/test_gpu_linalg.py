@@ -36,14 +36,20 @@ def test_pinv(m, n):
     rng = np.random.default_rng(1)
     A = rng.standard_normal((m, n))
     assert _rel(be.to_host(be.pinv(be.to_device(A))), np.linalg.pinv(A)) < 1e-11
-    if min(m, n) >= 5:  # rank deficient: same cut-off rule as lstsq(cond=None)
+    if min(m, n) >= 5:  # rank deficient, explicit cut-off (same rule as lstsq(cond=rcond): s <= rcond*s_max dropped)
         A[:, -1] = A[:, 0] * 2 - A[:, 1]
         if m <= n:
             A[-1] = A[0] + A[1]
         B = rng.standard_normal((m, 6))
-        want = scipy.linalg.lstsq(A, B)[0]
-        got = be.to_host(be.gemm(be.pinv(be.to_device(A)), be.to_device(B)))
+        want = scipy.linalg.lstsq(A, B, cond=1e-10)[0]
+        got = be.to_host(be.gemm(be.pinv(be.to_device(A), 1e-10), be.to_device(B)))
         assert _rel(got, want) < 1e-9
+        # a singular value well above eps*s_max is kept by the default cut-off, like gelsd
+        U, _, Vt = np.linalg.svd(rng.standard_normal((m, n)), full_matrices=False)
+        sv = np.logspace(0, -12, min(m, n))
+        A2 = (U * sv) @ Vt
+        got2 = be.to_host(be.pinv(be.to_device(A2)))
+        assert _rel(got2 @ A2 @ got2, got2) < 1e-3 and np.linalg.norm(got2, 2) > 1e11
 
 
 @pytest.mark.parametrize("m,n", [(1000, 20), (50, 50), (37, 5), (5, 1), (20000, 40)])

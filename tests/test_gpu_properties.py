@@ -83,8 +83,9 @@ def test_exact_recovery(fmt, method):
     from tt_sketch.tensor import CPTensor, DenseTensor, TensorTrain
 
     shape = (5, 6, 7, 4)
-    base = TensorTrain.random(shape, 2, seed=11)
+    base = TensorTrain.random(shape, 3, seed=11)
     dense = base.to_numpy()
+    rank = 3
     if fmt == "tt":
         X = base
     elif fmt == "cp":
@@ -98,13 +99,16 @@ def test_exact_recovery(fmt, method):
         other = CPTensor.random(shape, 2, seed=13)
         X = base + other + DenseTensor(dense).to_sparse()
         dense = 2 * dense + other.to_numpy()
-    lr, rr = (4, 6, 4), (6, 9, 7)
+        rank = 5
+    # left rank == exact TT rank (Omega has full row rank, like the reference's tests :269-306);
+    # an over-sized left rank makes Omega numerically singular and Omega^+ amplifies rounding.
+    lr, rr = (rank,) * 3, (2 * rank,) * 3
     if method == "stream":
         tt = stream_sketch(X, lr, rr, seed=5).to_tt()
     elif method == "orth":
         tt = orthogonal_sketch(X, lr, rr, seed=5)
     else:
-        tt = hmt_sketch(X, (5, 8, 4), seed=5)
+        tt = hmt_sketch(X, (rank + 2,) * 3, seed=5)
     err = np.linalg.norm(tt.to_numpy() - dense) / np.linalg.norm(dense)
     assert err < 1e-8, err
     if method == "orth":  # cores are left-orthogonal

@@ -840,13 +840,15 @@ extern "C" int ttsk_last_kernel_ms(ttsk_ctx* ctx, double* ms_total, double* ms_d
     return TTSK_OK;
 }
 
-// Host-buffer entry point: stage chunks through two pinned buffers, copy on a copy stream
-// while the previous chunk is sketched on the compute stream.
-extern "C" int ttsk_sparse_sketch_host(ttsk_ctx* ctx, int d, const int64_t* h_shape, int64_t nnz,
-                                       const int64_t* h_idx, int64_t idx_row_stride, const double* h_val,
-                                       const ttsk_drm* left, const ttsk_drm* right, double* h_out, int accumulate) {
+// Host-buffer entry points: the COO arrays live in (ideally pinned) host memory; chunks are
+// copied host->device on the context's copy stream into two staging buffers while the previous
+// chunk is sketched on the compute stream.  The packed sketch ends in d_out (device, for a
+// following all-reduce) and/or h_out (host).
+static int sparse_sketch_from_host(ttsk_ctx* ctx, int d, const int64_t* h_shape, int64_t nnz, const int64_t* h_idx,
+                                   int64_t idx_row_stride, const double* h_val, const ttsk_drm* left,
+                                   const ttsk_drm* right, double* d_out, double* h_out, int accumulate) {
     TTSK_TRY(validate_common(ctx, d, h_shape, nnz, left, right));
-    TTSK_ARG(h_out != nullptr && (nnz == 0 || (h_idx && h_val)), "NULL host pointer");
+    TTSK_ARG((h_out != nullptr || d_out != nullptr) && (nnz == 0 || (h_idx && h_val)), "NULL pointer");
     TTSK_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->compute_stream, cs = ctx->copy_stream;
     int32_t rL[TTSK_MAX_ORDER], rR[TTSK_MAX_ORDER];
@@ -880,7 +882,6 @@ extern "C" int ttsk_sparse_sketch_host(ttsk_ctx* ctx, int d, const int64_t* h_sh
         set_error("workspace carve failed");
         return TTSK_E_NOMEM;
     }
-    // The caller's buffers are pageable or pinned; register nothing, copy straight from them.
     SparsePlan pl;
     if (ctx->timing) TTSK_CUDA(cudaEventRecord(ctx->ev_t0, st));
     TTSK_TRY(build_plan(ctx, pl, d, h_shape, nnz, chunk, left, right, st));
@@ -888,7 +889,7 @@ extern "C" int ttsk_sparse_sketch_host(ttsk_ctx* ctx, int d, const int64_t* h_sh
     int buf = 0;
     for (int64_t c0 = 0; c0 < nnz; c0 += chunk, buf ^= 1) {
         const int64_t n = std::min<int64_t>(chunk, nnz - c0);
-        // wait until the kernels that read this staging buffer two chunks ago are done
+        // the staging buffer may be overwritten once the kernels that read it (two chunks ago) are done
         TTSK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[buf], 0));
         long long* di = (long long*)d_stage[buf];
         double* dv = (double*)(d_stage[buf] + (size_t)d * chunk * 8);
@@ -904,18 +905,40 @@ extern "C" int ttsk_sparse_sketch_host(ttsk_ctx* ctx, int d, const int64_t* h_sh
     }
     TTSK_TRY(edge_omegas(ctx, pl, d, h_shape, left, right, sk, st));
     if (ctx->timing) TTSK_CUDA(cudaEventRecord(ctx->ev_t1, st));
-    if (!accumulate) {
-        TTSK_CUDA(cudaMemcpyAsync(h_out, sk, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
-        TTSK_CUDA(cudaStreamSynchronize(st));
-    } else {
-        // accumulate on the host side of the boundary: bring the partial sketch back and add
-        std::vector<double> part((size_t)total);
-        TTSK_CUDA(cudaMemcpyAsync(part.data(), sk, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
-        TTSK_CUDA(cudaStreamSynchronize(st));
-        for (int64_t i = 0; i < total; i++) h_out[i] += part[(size_t)i];
+    if (d_out) {
+        if (accumulate) TTSK_TRY(axpy_launch(ctx, total, 1.0, sk, d_out, st));
+        else TTSK_CUDA(cudaMemcpyAsync(d_out, sk, (size_t)total * 8, cudaMemcpyDeviceToDevice, st));
     }
+    if (h_out) {
+        if (!accumulate) {
+            TTSK_CUDA(cudaMemcpyAsync(h_out, sk, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+            TTSK_CUDA(cudaStreamSynchronize(st));
+        } else {
+            std::vector<double> part((size_t)total);
+            TTSK_CUDA(cudaMemcpyAsync(part.data(), sk, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+            TTSK_CUDA(cudaStreamSynchronize(st));
+            for (int64_t i = 0; i < total; i++) h_out[i] += part[(size_t)i];
+        }
+    }
+    TTSK_CUDA(cudaStreamSynchronize(st));
     TTSK_CUDA(cudaStreamSynchronize(cs));
     return TTSK_OK;
+}
+
+extern "C" int ttsk_sparse_sketch_host(ttsk_ctx* ctx, int d, const int64_t* h_shape, int64_t nnz,
+                                       const int64_t* h_idx, int64_t idx_row_stride, const double* h_val,
+                                       const ttsk_drm* left, const ttsk_drm* right, double* h_out, int accumulate) {
+    TTSK_ARG(h_out != nullptr, "h_out is NULL");
+    return sparse_sketch_from_host(ctx, d, h_shape, nnz, h_idx, idx_row_stride, h_val, left, right, nullptr, h_out,
+                                   accumulate);
+}
+
+extern "C" int ttsk_sparse_sketch_stream(ttsk_ctx* ctx, int d, const int64_t* h_shape, int64_t nnz,
+                                         const int64_t* h_idx, int64_t idx_row_stride, const double* h_val,
+                                         const ttsk_drm* left, const ttsk_drm* right, double* d_out, int accumulate) {
+    TTSK_ARG(d_out != nullptr, "d_out is NULL");
+    return sparse_sketch_from_host(ctx, d, h_shape, nnz, h_idx, idx_row_stride, h_val, left, right, d_out, nullptr,
+                                   accumulate);
 }
 
 // ------------------------------------------------------------------ operator-level entry points
