@@ -166,13 +166,15 @@ def _c4_like(nnz, seed=0, shape=(10000, 10000, 10000, 500)):
     return shape, idx, val
 
 
-@pytest.mark.parametrize("kinds", [("gauss", "gauss"), ("tt", "tt"), ("gauss", "tt")])
-def test_sparse_c4_shape_vs_oracle(oracle_lib, kinds):
-    """BASELINE config 4's shape and ranks (rL=20, rR=40) at nnz=3e4: fused kernel vs oracle."""
+@pytest.mark.parametrize("kinds,nnz", [(("gauss", "gauss"), 30000), (("tt", "tt"), 30000), (("gauss", "tt"), 30000),
+                                       (("gauss", "gauss"), 150000)])
+def test_sparse_c4_shape_vs_oracle(oracle_lib, kinds, nnz):
+    """BASELINE config 4's shape and ranks (rL=20, rR=40): fused kernel vs oracle.  nnz=3e4 takes the
+    global-atomic bucket scatter, nnz=1.5e5 the two-level shared-memory scatter."""
     from oracle.sketch_oracle import Drm
     from tt_sketch.sketch import stream_sketch
 
-    shape, idx, val = _c4_like(30000)
+    shape, idx, val = _c4_like(nnz)
     d = len(shape)
     rl, rr = (20,) * 3, (40,) * 3
     ocores_l = oracle_lib.tt_drm_cores(shape, rl, 1, False) if kinds[0] == "tt" else []

@@ -47,19 +47,34 @@ struct Source {
     long long row_stride, col_stride;
 };
 
-struct PassParams {
-    int d;
+// The bucket scatter writes ONE packed word per nonzero in sorted order: (key << 32) | id with
+// key = i_mu and id = position in the chunk.  The pass kernel streams this array (coalesced)
+// and gathers the value / index rows of each nonzero itself: those random 8-byte reads run on
+// the otherwise idle memory pipes of an FP64-bound kernel instead of in a separate
+// bandwidth-bound sort kernel.
+struct ScatterParams {
     long long nnz;
+    const long long* key_idx;
+    int* cursor;
+    unsigned long long* keyid;
+};
+
+struct PassParams {
+    long long nnz;
+    long long n_mu;
+    const unsigned long long* keyid;  // sorted (key << 32 | id); nullptr: identity order, key 0
     const long long* idx[TTSK_MAX_ORDER];
     const double* val;
-    const int* perm;  // sorted order -> nonzero id (nullptr: identity)
-    const int* skey;  // sorted keys (nullptr: all zero)
-    long long n_mu;
     Source A, B, X;
-    int rA, rB, rX;  // logical tile heights (1 for SRC_NONE)
+    int rA, rB, rX;  // logical tile widths (1 for SRC_NONE)
     double* psi;     // (rA, n_mu, rB)
     double* omega;   // (rA, rX), only with X
-    int piece;
+    // shared-memory plan (host computed)
+    int pitchA, pitchB, pitchX;  // row pitch of each tile in doubles
+    int bufsA, bufsB, bufsX;     // 1, or 2 for gathered (cp.async double-buffered) sources
+    unsigned long long magicA, magicB, magicX;  // ceil(2^32 / r) for the e -> (p, a) split
+    int queue_cap;
+    int smem_bytes;
 };
 
 // ------------------------------------------------------------------ bucketing (counting sort)
@@ -67,6 +82,24 @@ __global__ void hist_kernel(const long long* __restrict__ idx, long long nnz, in
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nnz;
          p += (long long)gridDim.x * blockDim.x)
         atomicAdd(&hist[idx[p]], 1);
+}
+
+// shared-memory privatised histogram: each CTA counts a contiguous block of nonzeros in shared
+// memory and adds only its non-empty bins to the global histogram (n_mu <= kLocalBins)
+constexpr int kLocalBins = 26 * 1024;  // two int arrays of this size fit the 227 KB of one SM
+__global__ void __launch_bounds__(1024) hist_local_kernel(const long long* __restrict__ idx, long long nnz,
+                                                          long long block_len, int n_mu, int* __restrict__ hist) {
+    extern __shared__ int s_cnt[];
+    for (int k = threadIdx.x; k < n_mu; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    const long long b0 = (long long)blockIdx.x * block_len;
+    const long long b1 = (b0 + block_len < nnz) ? b0 + block_len : nnz;
+    for (long long p = b0 + threadIdx.x; p < b1; p += blockDim.x) atomicAdd(&s_cnt[idx[p]], 1);
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_mu; k += blockDim.x) {
+        const int c = s_cnt[k];
+        if (c) atomicAdd(&hist[k], c);
+    }
 }
 
 // exclusive scan of hist[0..n) into offs[0..n] (offs[n] = total) and a copy into cursor; one CTA.
@@ -108,14 +141,47 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ hist
     if (threadIdx.x == 0) offs[n] = s_carry;
 }
 
-__global__ void scatter_kernel(const long long* __restrict__ idx, long long nnz, int* __restrict__ cursor,
-                               int* __restrict__ perm, int* __restrict__ skey) {
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nnz;
+__device__ __forceinline__ unsigned long long fold_flat(const Source& f, const long long* const* idx,
+                                                        long long p) {
+    if (f.kind == SRC_ROWS) return (unsigned long long)p;
+    unsigned long long flat = 0;
+    for (int i = 0; i < f.k; i++)
+        flat += (unsigned long long)idx[f.modes[i]][p] * (unsigned long long)f.strides[i];
+    return flat;
+}
+
+__global__ void scatter_kernel(const ScatterParams S) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < S.nnz;
          p += (long long)gridDim.x * blockDim.x) {
-        const int key = (int)idx[p];
-        const int pos = atomicAdd(&cursor[key], 1);
-        perm[pos] = (int)p;
-        skey[pos] = key;
+        const int key = (int)S.key_idx[p];
+        const int pos = atomicAdd(&S.cursor[key], 1);
+        S.keyid[pos] = ((unsigned long long)(unsigned)key << 32) | (unsigned long long)(unsigned)p;
+    }
+}
+
+// Two-level scatter for n_mu <= kLocalBins: a CTA counts its contiguous block of nonzeros per
+// key in shared memory, reserves one global range per non-empty key (one atomic per key instead
+// of one per nonzero), then ranks its nonzeros with shared-memory atomics.
+__global__ void __launch_bounds__(1024) scatter_local_kernel(const ScatterParams S, long long block_len, int n_mu) {
+    extern __shared__ int s_bins[];
+    int* s_cnt = s_bins;
+    int* s_base = s_bins + n_mu;
+    for (int k = threadIdx.x; k < n_mu; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    const long long b0 = (long long)blockIdx.x * block_len;
+    const long long b1 = (b0 + block_len < S.nnz) ? b0 + block_len : S.nnz;
+    for (long long p = b0 + threadIdx.x; p < b1; p += blockDim.x) atomicAdd(&s_cnt[S.key_idx[p]], 1);
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_mu; k += blockDim.x) {
+        const int c = s_cnt[k];
+        s_base[k] = c ? atomicAdd(&S.cursor[k], c) : 0;
+        s_cnt[k] = 0;
+    }
+    __syncthreads();
+    for (long long p = b0 + threadIdx.x; p < b1; p += blockDim.x) {
+        const int key = (int)S.key_idx[p];
+        const int pos = s_base[key] + atomicAdd(&s_cnt[key], 1);
+        S.keyid[pos] = ((unsigned long long)(unsigned)key << 32) | (unsigned long long)(unsigned)p;
     }
 }
 
@@ -150,42 +216,77 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 constexpr int kPassThreads = 256;
 constexpr int kPassWarps = kPassThreads / 32;
+constexpr int kPiece = 512;  // sorted positions staged per CTA iteration
 
+// row pitch (doubles) of a tile with `tiles8` 8-wide MMA column tiles: == 8 (mod 16) so the
+// MMA fragment loads (4 rows x 8 columns per warp) are bank-conflict free
+__host__ __device__ constexpr int tile_pitch(int tiles8) { return 8 * tiles8 + ((tiles8 % 2 == 0) ? 8 : 0); }
+
+// gather TN rows of a ROWS/TABLE source into a [TN][pitch] tile with cp.async
 template <int TN>
-__device__ __forceinline__ void fill_source(const Source& S, int src_id, double* __restrict__ tile, int len,
-                                            const unsigned long long* __restrict__ s_flat,
-                                            const unsigned long long* __restrict__ s_salt,
-                                            const double* __restrict__ s_val, bool scale, int* __restrict__ s_queue,
-                                            int* __restrict__ s_qcount) {
-    constexpr int TNP = TN + 4;
+__device__ __forceinline__ void gather_rows_async(const Source& S, double* __restrict__ tile, int pitch,
+                                                  const unsigned long long* __restrict__ s_flat, int n_rows) {
+    const int tid = threadIdx.x;
+    const bool vec = (S.col_stride == 1) && ((S.r & 1) == 0) && ((S.row_stride & 1) == 0) &&
+                     ((reinterpret_cast<unsigned long long>(S.base) & 15ull) == 0);
+    if (vec) {
+        const int per_row = S.r >> 1;
+        const int total = n_rows * per_row;
+        for (int e = tid; e < total; e += kPassThreads) {
+            const int p = e / per_row, c = e - p * per_row;
+            cp_async16(tile + p * pitch + 2 * c, S.base + (long long)s_flat[p] * S.row_stride + 2 * c);
+        }
+    } else {
+        const int total = n_rows * S.r;
+        for (int e = tid; e < total; e += kPassThreads) {
+            const int p = e / S.r, a = e - p * S.r;
+            cp_async8(tile + p * pitch + a, S.base + (long long)s_flat[p] * S.row_stride + (long long)a * S.col_stride);
+        }
+    }
+}
+
+// hash-seeded Gaussian source -> [TN][pitch] tile: central branch inline, tails queued
+template <int TN>
+__device__ __forceinline__ void fill_gauss(const Source& S, unsigned long long magic, int src_id, double* __restrict__ tile,
+                                           int pitch, int len, const unsigned long long* __restrict__ s_flat,
+                                           const unsigned long long* __restrict__ s_salt, int* __restrict__ s_queue,
+                                           int* __restrict__ s_qcount) {
     const int tid = threadIdx.x, lane = tid & 31;
-    if (S.kind == SRC_GAUSS) {
-        const int total = S.r * TN;  // multiple of 32: whole warps stay together
-        for (int e0 = 0; e0 < total; e0 += kPassThreads) {
-            const int e = e0 + tid;
-            const bool in = e < total;
-            const int a = in ? e / TN : 0, p = e % TN;
-            bool tail = false;
-            int enc = 0;
-            if (in) {
-                double out = 0.0;
-                if (p < len) {
-                    const double u = uniform_from_hash(hash64(s_flat[p] + s_salt[a]));
-                    const int cls = ndtri_class(u);
-                    if (cls == 0) {
-                        out = ndtri_central(u);
-                        if (scale) out *= s_val[p];
-                    } else {
-                        out = u;
-                        tail = true;
-                        enc = (src_id << 28) | (cls << 26) | (a * TNP + p);
-                    }
-                }
-                tile[a * TNP + p] = out;
+    const int total = S.r * len;
+    const int total_pad = (total + 31) & ~31;
+    for (int e0 = 0; e0 < total_pad; e0 += kPassThreads) {
+        const int e = e0 + tid;
+        bool tail = false;
+        int enc = 0;
+        if (e < total) {
+            const int p = (int)(((unsigned long long)(unsigned)e * magic) >> 32);
+            const int a = e - p * S.r;
+            const double u = uniform_from_hash(hash64(s_flat[p] + s_salt[a]));
+            const int cls = ndtri_class(u);
+            const int off = p * pitch + a;
+            if (cls == 0) {
+                tile[off] = ndtri_central(u);
+            } else {
+                tile[off] = u;
+                tail = true;
+                enc = (src_id << 28) | (cls << 26) | off;
             }
+        }
+        if (e0 + (tid & ~31) < total) {  // warp-uniform: this warp still has items
             const unsigned m = __ballot_sync(0xffffffffu, tail);
             if (m) {
                 int base = 0;
@@ -194,219 +295,227 @@ __device__ __forceinline__ void fill_source(const Source& S, int src_id, double*
                 if (tail) s_queue[base + __popc(m & ((1u << lane) - 1u))] = enc;
             }
         }
-    } else if (S.kind == SRC_ROWS || S.kind == SRC_TABLE) {
-        const int total = S.r * TN;
-        for (int e = tid; e < total; e += kPassThreads) {
-            const int p = e / S.r, a = e - p * S.r;  // column fastest: row reads coalesce
-            double out = 0.0;
-            if (p < len) {
-                out = S.base[(long long)s_flat[p] * S.row_stride + (long long)a * S.col_stride];
-                if (scale) out *= s_val[p];
-            }
-            tile[a * TNP + p] = out;
-        }
     }
 }
 
-// MI/NJ: 8x8 MMA tiles covering rA / max(rB, rX).  HAS_X: also accumulate Omega = At Xt^T.
+// MI/NJ: 8x8 MMA tiles covering rA / max(rB, rX).  HAS_X: warps 4..7 accumulate
+// Omega = (v At)^T Xt while warps 0..3 accumulate Psi = (v At)^T Bt.
 template <int MI, int NJ, bool HAS_X, int TN>
 __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassParams P) {
-    constexpr int TNP = TN + 4;
-    constexpr int RAP = 8 * MI, RBP = 8 * NJ, RXP = HAS_X ? 8 * NJ : 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* s_tab = reinterpret_cast<double2*>(smem_raw);                       // 128 x 16 B
-    double* At = reinterpret_cast<double*>(s_tab + 128);                         // [RAP][TNP]
-    double* Bt = At + RAP * TNP;                                                 // [RBP][TNP]
-    double* Xt = Bt + RBP * TNP;                                                 // [RXP][TNP]
-    unsigned long long* s_salt = reinterpret_cast<unsigned long long*>(Xt + RXP * TNP);  // [RAP+RBP+RXP]
-    unsigned long long* s_flat = s_salt + (RAP + RBP + RXP);                     // [3][TN]
-    double* s_val = reinterpret_cast<double*>(s_flat + 3 * TN);                  // [TN]
-    int* s_queue = reinterpret_cast<int*>(s_val + TN);                           // [(RAP+RBP+RXP)*TN]
-    int* s_misc = s_queue + (RAP + RBP + RXP) * TN;                              // len, key, qcount
+    const int PA = P.pitchA, PB = P.pitchB, PX = P.pitchX;
+    double2* s_tab = reinterpret_cast<double2*>(smem_raw);  // 128 x 16 B
+    double* s_val = reinterpret_cast<double*>(s_tab + 128);  // [kPiece]
+    unsigned long long* s_fa = reinterpret_cast<unsigned long long*>(s_val + kPiece);
+    unsigned long long* s_fb = s_fa + kPiece;
+    unsigned long long* s_fx = s_fb + kPiece;
+    unsigned long long* s_salt = s_fx + kPiece;              // [3][64]
+    double* At = reinterpret_cast<double*>(s_salt + 192);    // [bufsA][TN][PA]
+    double* Bt = At + P.bufsA * TN * PA;
+    double* Xt = Bt + P.bufsB * TN * PB;
+    int* s_key = reinterpret_cast<int*>(Xt + (HAS_X ? P.bufsX * TN * PX : 0));  // [kPiece]
+    int* s_queue = s_key + kPiece;                           // [queue_cap]
+    int* s_misc = s_queue + P.queue_cap;                     // qcount
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
+    const bool gatherA = (P.A.kind == SRC_ROWS || P.A.kind == SRC_TABLE);
+    const bool gatherB = (P.B.kind == SRC_ROWS || P.B.kind == SRC_TABLE);
+    const bool gatherX = HAS_X && (P.X.kind == SRC_ROWS || P.X.kind == SRC_TABLE);
 
     load_logtab(s_tab);
-    for (int i = tid; i < (RAP + RBP + RXP) * TNP; i += kPassThreads) At[i] = 0.0;
+    {
+        const int tile_doubles = P.bufsA * TN * PA + P.bufsB * TN * PB + (HAS_X ? P.bufsX * TN * PX : 0);
+        for (int i = tid; i < tile_doubles; i += kPassThreads) At[i] = 0.0;
+    }
     if (P.A.kind == SRC_GAUSS)
         for (int a = tid; a < P.A.r; a += kPassThreads)
             s_salt[a] = hash64((unsigned long long)(P.A.rank_min + a)) + P.A.seed;
     if (P.B.kind == SRC_GAUSS)
         for (int a = tid; a < P.B.r; a += kPassThreads)
-            s_salt[RAP + a] = hash64((unsigned long long)(P.B.rank_min + a)) + P.B.seed;
+            s_salt[64 + a] = hash64((unsigned long long)(P.B.rank_min + a)) + P.B.seed;
     if (HAS_X && P.X.kind == SRC_GAUSS)
         for (int a = tid; a < P.X.r; a += kPassThreads)
-            s_salt[RAP + RBP + a] = hash64((unsigned long long)(P.X.rank_min + a)) + P.X.seed;
+            s_salt[128 + a] = hash64((unsigned long long)(P.X.rank_min + a)) + P.X.seed;
+
+    // role of this warp in the accumulate stage
+    const bool omega_role = HAS_X && warp >= kPassWarps / 2;
+    const int role_warps = HAS_X ? kPassWarps / 2 : kPassWarps;
+    const int role_rank = HAS_X ? (warp & (kPassWarps / 2 - 1)) : warp;
 
     double acc[MI][NJ][2];
-    double acc_o[HAS_X ? MI : 1][HAS_X ? NJ : 1][2];
 #pragma unroll
     for (int i = 0; i < MI; i++)
 #pragma unroll
         for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    if (HAS_X) {
-#pragma unroll
-        for (int i = 0; i < (HAS_X ? MI : 1); i++)
-#pragma unroll
-            for (int j = 0; j < (HAS_X ? NJ : 1); j++) acc_o[i][j][0] = acc_o[i][j][1] = 0.0;
-    }
-    __syncthreads();
 
-    auto flush_psi = [&](long long key) {
+    auto flush = [&](double* dst_base, long long row_pitch, int ncols) {
 #pragma unroll
         for (int i = 0; i < MI; i++)
 #pragma unroll
             for (int j = 0; j < NJ; j++) {
                 const int row = 8 * i + g, col = 8 * j + 2 * q;
                 if (row < P.rA) {
-                    double* dst = P.psi + ((long long)row * P.n_mu + key) * P.rB + col;
-                    if (col < P.rB && acc[i][j][0] != 0.0) atomicAdd(dst, acc[i][j][0]);
-                    if (col + 1 < P.rB && acc[i][j][1] != 0.0) atomicAdd(dst + 1, acc[i][j][1]);
+                    double* dst = dst_base + (long long)row * row_pitch + col;
+                    if (col < ncols && acc[i][j][0] != 0.0) atomicAdd(dst, acc[i][j][0]);
+                    if (col + 1 < ncols && acc[i][j][1] != 0.0) atomicAdd(dst + 1, acc[i][j][1]);
                 }
                 acc[i][j][0] = acc[i][j][1] = 0.0;
             }
     };
+    auto flush_psi = [&](long long key) {
+        if (!omega_role) flush(P.psi + key * P.rB, (long long)P.n_mu * P.rB, P.rB);
+    };
 
-    const long long n_pieces = (P.nnz + P.piece - 1) / P.piece;
+    const long long n_pieces = (P.nnz + kPiece - 1) / kPiece;
     for (long long piece = blockIdx.x; piece < n_pieces; piece += gridDim.x) {
-        const long long s = piece * P.piece;
-        const long long e = (s + P.piece < P.nnz) ? s + P.piece : P.nnz;
+        const long long s = piece * kPiece;
+        const int n_piece = (int)((s + kPiece < P.nnz) ? kPiece : P.nnz - s);
+        __syncthreads();  // previous piece fully consumed (tiles, records, queue)
+        // ---- stage the piece: stream the sorted (key, id) words, gather value and index rows
+        for (int i = tid; i < kPiece; i += kPassThreads) {
+            const bool in = i < n_piece;
+            long long id = s + i;
+            int key = in ? 0 : -1;
+            if (in && P.keyid) {
+                const unsigned long long w = P.keyid[s + i];
+                id = (long long)(w & 0xffffffffull);
+                key = (int)(w >> 32);
+            }
+            s_key[i] = key;
+            s_val[i] = in ? P.val[id] : 0.0;
+            if (P.A.kind != SRC_NONE) s_fa[i] = in ? fold_flat(P.A, P.idx, id) : 0ull;
+            if (P.B.kind != SRC_NONE) s_fb[i] = in ? fold_flat(P.B, P.idx, id) : 0ull;
+            if (HAS_X) s_fx[i] = in ? fold_flat(P.X, P.idx, id) : 0ull;
+        }
+        if (tid == 0) s_misc[0] = 0;
+        __syncthreads();
         long long cur_key = -1;
-        long long c = s;
-        while (c < e) {
-            // ---- tile header: run of equal keys starting at c, at most TN long
-            if (warp == 0) {
-                int len = 0;
-                long long key0 = 0;
-                if (P.skey == nullptr) {
-                    len = (int)((e - c < TN) ? e - c : TN);
-                } else {
-                    key0 = P.skey[c];
-                    bool open = true;
+        int c = 0, buf = 0;
+        // gather of the first tile
+        {
+            const int rows = (n_piece < TN) ? n_piece : TN;
+            if (gatherA) gather_rows_async<TN>(P.A, At, PA, s_fa, rows);
+            if (gatherB) gather_rows_async<TN>(P.B, Bt, PB, s_fb, rows);
+            if (gatherX) gather_rows_async<TN>(P.X, Xt, PX, s_fx, rows);
+            cp_async_commit();
+        }
+        while (c < n_piece) {
+            // ---- run of equal keys starting at c, at most TN long (every warp computes it)
+            int len = 0;
+            const int key0 = s_key[c];
+            {
+                bool open = true;
 #pragma unroll
-                    for (int t = 0; t < TN / 32; t++) {
-                        const long long pos = c + t * 32 + lane;
-                        const bool same = (pos < e) && (P.skey[pos] == (int)key0);
-                        const unsigned m = __ballot_sync(0xffffffffu, same);
-                        if (open) {
-                            if (m == 0xffffffffu) len += 32;
-                            else { len += __ffs(~m) - 1; open = false; }
-                        }
+                for (int t = 0; t < TN / 32; t++) {
+                    const int pos = c + t * 32 + lane;
+                    const bool same = (pos < n_piece) && (s_key[pos] == key0);
+                    const unsigned m = __ballot_sync(0xffffffffu, same);
+                    if (open) {
+                        if (m == 0xffffffffu) len += 32;
+                        else { len += __ffs(~m) - 1; open = false; }
                     }
                 }
-                if (lane == 0) { s_misc[0] = len; s_misc[1] = (int)key0; s_misc[2] = 0; }
             }
-            __syncthreads();
-            const int len = s_misc[0];
-            const long long key = s_misc[1];
-            if (key != cur_key) {
+            const int next_c = c + len;
+            // ---- prefetch the gathered rows of the NEXT tile, then wait for this tile's
+            if (next_c < n_piece) {
+                const int rows = (n_piece - next_c < TN) ? n_piece - next_c : TN;
+                const int nb = buf ^ 1;
+                if (gatherA) gather_rows_async<TN>(P.A, At + nb * TN * PA, PA, s_fa + next_c, rows);
+                if (gatherB) gather_rows_async<TN>(P.B, Bt + nb * TN * PB, PB, s_fb + next_c, rows);
+                if (gatherX) gather_rows_async<TN>(P.X, Xt + nb * TN * PX, PX, s_fx + next_c, rows);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();
+            if ((long long)key0 != cur_key) {
                 if (cur_key >= 0) flush_psi(cur_key);
-                cur_key = key;
+                cur_key = key0;
             }
-            // ---- per-nonzero metadata
-            if (tid < TN) {
-                double v = 0.0;
-                unsigned long long fa = 0, fb = 0, fx = 0;
-                if (tid < len) {
-                    const long long id = P.perm ? (long long)P.perm[c + tid] : c + tid;
-                    v = P.val[id];
-                    if (P.A.kind == SRC_ROWS) fa = (unsigned long long)id;
-                    else if (P.A.kind != SRC_NONE)
-                        for (int i = 0; i < P.A.k; i++)
-                            fa += (unsigned long long)P.idx[P.A.modes[i]][id] * (unsigned long long)P.A.strides[i];
-                    if (P.B.kind == SRC_ROWS) fb = (unsigned long long)id;
-                    else if (P.B.kind != SRC_NONE)
-                        for (int i = 0; i < P.B.k; i++)
-                            fb += (unsigned long long)P.idx[P.B.modes[i]][id] * (unsigned long long)P.B.strides[i];
-                    if (HAS_X) {
-                        if (P.X.kind == SRC_ROWS) fx = (unsigned long long)id;
-                        else
-                            for (int i = 0; i < P.X.k; i++)
-                                fx += (unsigned long long)P.idx[P.X.modes[i]][id] * (unsigned long long)P.X.strides[i];
-                    }
-                }
-                s_val[tid] = v;
-                s_flat[tid] = fa;
-                s_flat[TN + tid] = fb;
-                s_flat[2 * TN + tid] = fx;
-                if (P.A.kind == SRC_NONE) At[tid] = v;                      // Psi_0: 1 x rB, scaled by v
-                if (P.B.kind == SRC_NONE) Bt[tid] = (tid < len) ? 1.0 : 0.0;  // Psi_{d-1}: rA x 1
-            }
-            __syncthreads();
-            // ---- sources -> tiles (central branch inline, tails queued)
-            fill_source<TN>(P.A, 0, At, len, s_flat, s_salt, s_val, true, s_queue, &s_misc[2]);
-            fill_source<TN>(P.B, 1, Bt, len, s_flat + TN, s_salt + RAP, s_val, false, s_queue, &s_misc[2]);
-            if (HAS_X)
-                fill_source<TN>(P.X, 2, Xt, len, s_flat + 2 * TN, s_salt + RAP + RBP, s_val, false, s_queue,
-                                &s_misc[2]);
+            double* At_c = At + (P.bufsA == 2 ? buf * TN * PA : 0);
+            double* Bt_c = Bt + (P.bufsB == 2 ? buf * TN * PB : 0);
+            double* Xt_c = Xt + (HAS_X && P.bufsX == 2 ? buf * TN * PX : 0);
+            // ---- on-the-fly sources (central branch inline, tails queued)
+            if (P.A.kind == SRC_GAUSS)
+                fill_gauss<TN>(P.A, P.magicA, 0, At_c, PA, len, s_fa + c, s_salt, s_queue, &s_misc[0]);
+            else if (P.A.kind == SRC_NONE && tid < TN) At_c[tid * PA] = 1.0;
+            if (P.B.kind == SRC_GAUSS)
+                fill_gauss<TN>(P.B, P.magicB, 1, Bt_c, PB, len, s_fb + c, s_salt + 64, s_queue, &s_misc[0]);
+            else if (P.B.kind == SRC_NONE && tid < TN) Bt_c[tid * PB] = 1.0;
+            if (HAS_X && P.X.kind == SRC_GAUSS)
+                fill_gauss<TN>(P.X, P.magicX, 2, Xt_c, PX, len, s_fx + c, s_salt + 128, s_queue, &s_misc[0]);
             __syncthreads();
             // ---- deferred tails, dense over the queue
             {
-                const int nq = s_misc[2];
+                const int nq = s_misc[0];
                 for (int qi = tid; qi < nq; qi += kPassThreads) {
                     const int enc = s_queue[qi];
                     const int src = enc >> 28, cls = (enc >> 26) & 3, off = enc & 0x3ffffff;
-                    double* tile = src == 0 ? At : (src == 1 ? Bt : Xt);
-                    double out = ndtri_tail(tile[off], cls, s_tab);
-                    if (src == 0) out *= s_val[off % TNP];
-                    tile[off] = out;
+                    double* tile = src == 0 ? At_c : (src == 1 ? Bt_c : Xt_c);
+                    tile[off] = ndtri_tail(tile[off], cls, s_tab);
                 }
             }
             __syncthreads();
-            // ---- accumulate: each warp takes k-chunks of 4 nonzeros
-            for (int ch = warp; ch * 4 < len; ch += kPassWarps) {
-                const int p0 = ch * 4 + q;
-                double a[MI], b[NJ];
+            if (tid == 0) s_misc[0] = 0;
+            // ---- accumulate: k-chunks of 4 nonzeros; A fragment scaled by the value
+            {
+                const double* Rt = omega_role ? Xt_c : Bt_c;
+                const int PR = omega_role ? PX : PB;
+                for (int ch = role_rank; ch * 4 < len; ch += role_warps) {
+                    const int p0 = ch * 4 + q;
+                    const double v = (p0 < len) ? s_val[c + p0] : 0.0;
+                    double a[MI], b[NJ];
 #pragma unroll
-                for (int i = 0; i < MI; i++) a[i] = At[(8 * i + g) * TNP + p0];
+                    for (int i = 0; i < MI; i++) a[i] = At_c[p0 * PA + 8 * i + g] * v;
 #pragma unroll
-                for (int j = 0; j < NJ; j++) b[j] = Bt[(8 * j + g) * TNP + p0];
+                    for (int j = 0; j < NJ; j++) b[j] = Rt[p0 * PR + 8 * j + g];
 #pragma unroll
-                for (int i = 0; i < MI; i++)
+                    for (int i = 0; i < MI; i++)
 #pragma unroll
-                    for (int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                if (HAS_X) {
-#pragma unroll
-                    for (int j = 0; j < NJ; j++) b[j] = Xt[(8 * j + g) * TNP + p0];
-#pragma unroll
-                    for (int i = 0; i < (HAS_X ? MI : 1); i++)
-#pragma unroll
-                        for (int j = 0; j < (HAS_X ? NJ : 1); j++)
-                            dmma(acc_o[i][j][0], acc_o[i][j][1], a[i], b[j]);
+                        for (int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                 }
             }
-            c += len;
+            __syncthreads();
+            c = next_c;
+            buf ^= 1;
         }
+        cp_async_wait<0>();
         if (cur_key >= 0) flush_psi(cur_key);
     }
-    if (HAS_X) {
-#pragma unroll
-        for (int i = 0; i < (HAS_X ? MI : 1); i++)
-#pragma unroll
-            for (int j = 0; j < (HAS_X ? NJ : 1); j++) {
-                const int row = 8 * i + g, col = 8 * j + 2 * q;
-                if (row < P.rA) {
-                    double* dst = P.omega + (long long)row * P.rX + col;
-                    if (col < P.rX && acc_o[i][j][0] != 0.0) atomicAdd(dst, acc_o[i][j][0]);
-                    if (col + 1 < P.rX && acc_o[i][j][1] != 0.0) atomicAdd(dst + 1, acc_o[i][j][1]);
-                }
-            }
-    }
+    if (omega_role) flush(P.omega, P.rX, P.rX);
 }
 
 template <int MI, int NJ, bool HAS_X, int TN>
-static int launch_pass_t(ttsk_ctx* ctx, const PassParams& P, cudaStream_t st) {
-    constexpr int TNP = TN + 4;
-    constexpr int R = 8 * MI + 8 * NJ + (HAS_X ? 8 * NJ : 0);
-    const size_t smem = 128 * 16 + (size_t)R * TNP * 8 + (size_t)R * 8 + 3 * TN * 8 + TN * 8 +
-                        (size_t)R * TN * 4 + 16;
+static int launch_pass_t(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     auto kern = sparse_pass_kernel<MI, NJ, HAS_X, TN>;
+    auto gathered = [](const Source& S) { return S.kind == SRC_ROWS || S.kind == SRC_TABLE; };
+    P.pitchA = tile_pitch(MI);
+    P.pitchB = tile_pitch(NJ);
+    P.pitchX = tile_pitch(NJ);
+    P.bufsA = gathered(P.A) ? 2 : 1;
+    P.bufsB = gathered(P.B) ? 2 : 1;
+    P.bufsX = HAS_X ? (gathered(P.X) ? 2 : 1) : 0;
+    auto magic = [](int r) { return (((unsigned long long)1 << 32) + (unsigned)r - 1) / (unsigned)r; };
+    P.magicA = magic(P.A.r > 0 ? P.A.r : 1);
+    P.magicB = magic(P.B.r > 0 ? P.B.r : 1);
+    P.magicX = magic(P.X.r > 0 ? P.X.r : 1);
+    int otf_cols = 0;
+    if (P.A.kind == SRC_GAUSS) otf_cols += P.A.r;
+    if (P.B.kind == SRC_GAUSS) otf_cols += P.B.r;
+    if (HAS_X && P.X.kind == SRC_GAUSS) otf_cols += P.X.r;
+    P.queue_cap = otf_cols * TN + 32;
+    const size_t tile_doubles = (size_t)P.bufsA * TN * P.pitchA + (size_t)P.bufsB * TN * P.pitchB +
+                                (size_t)P.bufsX * TN * P.pitchX;
+    const size_t smem = 128 * 16 + (size_t)kPiece * 8 * 4 + 192 * 8 + tile_doubles * 8 + (size_t)kPiece * 4 +
+                        (size_t)P.queue_cap * 4 + 64;
+    P.smem_bytes = (int)smem;
+    TTSK_ARG(smem <= 227 * 1024, "sparse pass: shared-memory plan exceeds 227 KB (ranks too large)");
     TTSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TTSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 1;
     TTSK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPassThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    const long long n_pieces = (P.nnz + P.piece - 1) / P.piece;
+    const long long n_pieces = (P.nnz + kPiece - 1) / kPiece;
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > n_pieces) grid = n_pieces;
     if (grid < 1) grid = 1;
@@ -416,11 +525,11 @@ static int launch_pass_t(ttsk_ctx* ctx, const PassParams& P, cudaStream_t st) {
 }
 
 template <bool HAS_X>
-static int launch_pass_x(ttsk_ctx* ctx, const PassParams& P, cudaStream_t st) {
+static int launch_pass_x(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     const int mi = (P.rA + 7) / 8;
     const int nj = (std::max(P.rB, HAS_X ? P.rX : 1) + 7) / 8;
     TTSK_ARG(mi <= 8 && nj <= 8, "sparse pass: DRM rank above 64 is not supported by the fused kernel");
-#define TTSK_PASS(MI_, NJ_) return launch_pass_t<MI_, NJ_, HAS_X, 32>(ctx, P, st)
+#define TTSK_PASS(MI_, NJ_) return launch_pass_t<MI_, NJ_, HAS_X, 64>(ctx, P, st)
     const int MIr = mi <= 1 ? 1 : (mi <= 3 ? 3 : (mi <= 5 ? 5 : 8));
     const int NJr = nj <= 1 ? 1 : (nj <= 3 ? 3 : (nj <= 5 ? 5 : 8));
     switch (MIr * 10 + NJr) {
@@ -446,9 +555,65 @@ static int launch_pass_x(ttsk_ctx* ctx, const PassParams& P, cudaStream_t st) {
     return TTSK_E_ARG;
 }
 
-static int launch_pass(ttsk_ctx* ctx, const PassParams& P, bool has_x, cudaStream_t st) {
+static int launch_pass(ttsk_ctx* ctx, PassParams& P, bool has_x, cudaStream_t st) {
     if (P.nnz <= 0) return TTSK_OK;
     return has_x ? launch_pass_x<true>(ctx, P, st) : launch_pass_x<false>(ctx, P, st);
+}
+
+// ---- sort buffers (workspace views) and the bucket pass
+struct SortBufs {
+    int* hist; int* offs; int* cursor;
+    unsigned long long* keyid;
+};
+static int64_t sortbufs_bytes(int64_t n_max, int64_t chunk) {
+    return 3 * align_up((n_max + 1) * 4, 256) + align_up(chunk * 8, 256) + 2048;
+}
+static int carve_sortbufs(ttsk_ctx* ctx, SortBufs& sb, int64_t n_max, int64_t chunk) {
+    sb.hist = (int*)ctx->ws_alloc((n_max + 1) * 4);
+    sb.offs = (int*)ctx->ws_alloc((n_max + 1) * 4);
+    sb.cursor = (int*)ctx->ws_alloc((n_max + 1) * 4);
+    sb.keyid = (unsigned long long*)ctx->ws_alloc(chunk * 8);
+    if (!sb.hist || !sb.offs || !sb.cursor || !sb.keyid) {
+        set_error("workspace carve failed (sort buffers)");
+        return TTSK_E_NOMEM;
+    }
+    return TTSK_OK;
+}
+
+// bucket the chunk by the index row `key_idx`: sb.keyid receives (key << 32 | id) in sorted order
+static int sort_keys(ttsk_ctx* ctx, int64_t nnz, const long long* key_idx, int64_t n_mu, SortBufs& sb,
+                     cudaStream_t st) {
+    long long blocks = (nnz + 255) / 256;
+    if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
+    const bool local = n_mu <= kLocalBins && nnz >= 65536;
+    long long block_len = (nnz + 2LL * ctx->sm_count - 1) / (2LL * ctx->sm_count);
+    if (block_len < 65536) block_len = 65536;
+    const long long local_grid = (nnz + block_len - 1) / block_len;
+    TTSK_CUDA(cudaMemsetAsync(sb.hist, 0, (size_t)n_mu * sizeof(int), st));
+    if (local) {
+        const size_t smem = (size_t)n_mu * 4;
+        TTSK_CUDA(cudaFuncSetAttribute(hist_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hist_local_kernel<<<(unsigned)local_grid, 1024, smem, st>>>(key_idx, nnz, block_len, (int)n_mu, sb.hist);
+    } else {
+        hist_kernel<<<(unsigned)blocks, 256, 0, st>>>(key_idx, nnz, sb.hist);
+    }
+    TTSK_LAUNCHED(ctx);
+    scan_kernel<<<1, 1024, 0, st>>>(sb.hist, n_mu, sb.offs, sb.cursor);
+    TTSK_LAUNCHED(ctx);
+    ScatterParams S;
+    S.nnz = nnz;
+    S.key_idx = key_idx;
+    S.cursor = sb.cursor;
+    S.keyid = sb.keyid;
+    if (local) {
+        const size_t smem = (size_t)n_mu * 8;
+        TTSK_CUDA(cudaFuncSetAttribute(scatter_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        scatter_local_kernel<<<(unsigned)local_grid, 1024, smem, st>>>(S, block_len, (int)n_mu);
+    } else {
+        scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(S);
+    }
+    TTSK_LAUNCHED(ctx);
+    return TTSK_OK;
 }
 
 // ------------------------------------------------------------------ host-side planning
@@ -514,20 +679,6 @@ struct SideState {
     double* chain[TTSK_MAX_ORDER];     // TT: per-level chain buffers (chunk x true rank), DRM orientation
 };
 
-static int bucket_mode(ttsk_ctx* ctx, const long long* d_idx_mu, int64_t nnz, int64_t n_mu, int* d_hist,
-                       int* d_offs, int* d_cursor, int* d_perm, int* d_skey, cudaStream_t st) {
-    TTSK_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)n_mu * sizeof(int), st));
-    long long blocks = (nnz + 255) / 256;
-    if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
-    hist_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_idx_mu, nnz, d_hist);
-    TTSK_LAUNCHED(ctx);
-    scan_kernel<<<1, 1024, 0, st>>>(d_hist, n_mu, d_offs, d_cursor);
-    TTSK_LAUNCHED(ctx);
-    scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_idx_mu, nnz, d_cursor, d_perm, d_skey);
-    TTSK_LAUNCHED(ctx);
-    return TTSK_OK;
-}
-
 static int ttdrm_step(ttsk_ctx* ctx, int64_t nnz, const long long* idx_mu, const double* v_in, int r_in,
                       const double* core, int64_t n, int r_out, double* v_out, cudaStream_t st) {
     if (nnz <= 0) return TTSK_OK;
@@ -573,7 +724,7 @@ struct SparsePlan {
 };
 
 static int64_t chunk_bytes_per_nnz(int d, const ttsk_drm* left, const ttsk_drm* right) {
-    int64_t b = 8;  // perm + skey
+    int64_t b = 8;  // sorted (key, id) words
     if (left->kind == TTSK_DRM_TT)
         for (int k = 0; k < d - 1; k++) b += 8LL * left->core_r1[k];
     if (right->kind == TTSK_DRM_TT)
@@ -583,8 +734,7 @@ static int64_t chunk_bytes_per_nnz(int d, const ttsk_drm* left, const ttsk_drm* 
 
 static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* shape, int64_t nnz,
                         const int64_t* d_idx, int64_t idx_row_stride, const double* d_val, const ttsk_drm* left,
-                        const ttsk_drm* right, double* out, int* d_hist, int* d_offs, int* d_cursor, int* d_perm,
-                        int* d_skey, cudaStream_t st) {
+                        const ttsk_drm* right, double* out, SortBufs& sb, cudaStream_t st) {
     if (nnz <= 0) return TTSK_OK;
     const SketchLayout& lay = pl.lay;
     // TT-DRM chains for this chunk (tensor_train_drm.py:60-69)
@@ -598,18 +748,13 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
             TTSK_TRY(ttdrm_step(ctx, nnz, (const long long*)(d_idx + (d - 1 - k) * idx_row_stride),
                                 k == 0 ? nullptr : pl.right.chain[k - 1], right->core_r0[k], right->d_cores[k],
                                 shape[d - 1 - k], right->core_r1[k], pl.right.chain[k], st));
+    const long long* idx_rows[TTSK_MAX_ORDER];
+    for (int m = 0; m < d; m++) idx_rows[m] = (const long long*)(d_idx + m * idx_row_stride);
     for (int mu = 0; mu < d; mu++) {
         PassParams P;
         std::memset(&P, 0, sizeof(P));
-        P.d = d;
         P.nnz = nnz;
-        for (int m = 0; m < d; m++) P.idx[m] = (const long long*)(d_idx + m * idx_row_stride);
-        P.val = d_val;
         P.n_mu = shape[mu];
-        TTSK_TRY(bucket_mode(ctx, P.idx[mu], nnz, shape[mu], d_hist, d_offs, d_cursor, d_perm, d_skey, st));
-        P.perm = d_perm;
-        P.skey = d_skey;
-        P.piece = 2048;
         P.A.kind = SRC_NONE; P.B.kind = SRC_NONE; P.X.kind = SRC_NONE;
         P.rA = lay.r1(mu);
         P.rB = lay.r2(mu);
@@ -622,6 +767,10 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
             P.rX = lay.rR[mu - 1];
             P.omega = out + lay.omega_off[mu - 1];
         }
+        TTSK_TRY(sort_keys(ctx, nnz, idx_rows[mu], shape[mu], sb, st));
+        P.keyid = sb.keyid;
+        for (int m = 0; m < d; m++) P.idx[m] = idx_rows[m];
+        P.val = d_val;
         P.psi = out + lay.psi_off[mu];
         if (ctx->timing) {
             while ((int)ctx->ev_pass.size() < 2 * (ctx->n_pass_events + 1)) {
@@ -702,8 +851,7 @@ static int64_t plan_workspace_bytes(int d, const int64_t* shape, int64_t nnz_tot
     int64_t bytes = 0;
     auto add = [&](int64_t b) { bytes = align_up(bytes, 256) + b; };
     add(sketch_elems * 8);                  // temp sketch when accumulating
-    add((n_max + 1) * 4); add((n_max + 1) * 4); add((n_max + 1) * 4);  // hist, offs, cursor
-    add(chunk * 4); add(chunk * 4);         // perm, skey
+    add(sortbufs_bytes(n_max, chunk));      // hist/offs/cursor + sorted records
     const int64_t table_rows_cap = std::max<int64_t>(nnz_total / 4, 1);
     for (int side = 0; side < 2; side++) {
         const ttsk_drm* drm = side == 0 ? left : right;
@@ -800,12 +948,9 @@ extern "C" int ttsk_sparse_sketch(ttsk_ctx* ctx, int d, const int64_t* h_shape, 
     double* tmp = (double*)ctx->ws_alloc(total * 8);
     int64_t n_max = 0;
     for (int mu = 0; mu < d; mu++) n_max = std::max<int64_t>(n_max, h_shape[mu]);
-    int* d_hist = (int*)ctx->ws_alloc((n_max + 1) * 4);
-    int* d_offs = (int*)ctx->ws_alloc((n_max + 1) * 4);
-    int* d_cursor = (int*)ctx->ws_alloc((n_max + 1) * 4);
-    int* d_perm = (int*)ctx->ws_alloc(chunk * 4);
-    int* d_skey = (int*)ctx->ws_alloc(chunk * 4);
-    if (!tmp || !d_hist || !d_offs || !d_cursor || !d_perm || !d_skey) {
+    SortBufs sb;
+    TTSK_TRY(carve_sortbufs(ctx, sb, n_max, chunk));
+    if (!tmp) {
         set_error("workspace carve failed");
         return TTSK_E_NOMEM;
     }
@@ -815,8 +960,7 @@ extern "C" int ttsk_sparse_sketch(ttsk_ctx* ctx, int d, const int64_t* h_shape, 
     TTSK_CUDA(cudaMemsetAsync(sk, 0, (size_t)total * 8, st));
     for (int64_t c0 = 0; c0 < nnz; c0 += chunk) {
         const int64_t n = std::min<int64_t>(chunk, nnz - c0);
-        TTSK_TRY(sparse_chunk(ctx, pl, d, h_shape, n, d_idx + c0, idx_row_stride, d_val + c0, left, right, sk, d_hist,
-                              d_offs, d_cursor, d_perm, d_skey, st));
+        TTSK_TRY(sparse_chunk(ctx, pl, d, h_shape, n, d_idx + c0, idx_row_stride, d_val + c0, left, right, sk, sb, st));
     }
     TTSK_TRY(edge_omegas(ctx, pl, d, h_shape, left, right, sk, st));
     if (accumulate) TTSK_TRY(axpy_launch(ctx, total, 1.0, tmp, d_out, st));
@@ -873,12 +1017,9 @@ static int sparse_sketch_from_host(ttsk_ctx* ctx, int d, const int64_t* h_shape,
     double* sk = (double*)ctx->ws_alloc(total * 8);
     int64_t n_max = 0;
     for (int mu = 0; mu < d; mu++) n_max = std::max<int64_t>(n_max, h_shape[mu]);
-    int* d_hist = (int*)ctx->ws_alloc((n_max + 1) * 4);
-    int* d_offs = (int*)ctx->ws_alloc((n_max + 1) * 4);
-    int* d_cursor = (int*)ctx->ws_alloc((n_max + 1) * 4);
-    int* d_perm = (int*)ctx->ws_alloc(chunk * 4);
-    int* d_skey = (int*)ctx->ws_alloc(chunk * 4);
-    if (!d_stage[0] || !d_stage[1] || !sk || !d_hist || !d_offs || !d_cursor || !d_perm || !d_skey) {
+    SortBufs sb;
+    TTSK_TRY(carve_sortbufs(ctx, sb, n_max, chunk));
+    if (!d_stage[0] || !d_stage[1] || !sk) {
         set_error("workspace carve failed");
         return TTSK_E_NOMEM;
     }
@@ -899,8 +1040,7 @@ static int sparse_sketch_from_host(ttsk_ctx* ctx, int d, const int64_t* h_shape,
         TTSK_CUDA(cudaMemcpyAsync(dv, h_val + c0, (size_t)n * 8, cudaMemcpyHostToDevice, cs));
         TTSK_CUDA(cudaEventRecord(ctx->ev_copy[buf], cs));
         TTSK_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy[buf], 0));
-        TTSK_TRY(sparse_chunk(ctx, pl, d, h_shape, n, (const int64_t*)di, chunk, dv, left, right, sk, d_hist, d_offs,
-                              d_cursor, d_perm, d_skey, st));
+        TTSK_TRY(sparse_chunk(ctx, pl, d, h_shape, n, (const int64_t*)di, chunk, dv, left, right, sk, sb, st));
         TTSK_CUDA(cudaEventRecord(ctx->ev_done[buf], st));
     }
     TTSK_TRY(edge_omegas(ctx, pl, d, h_shape, left, right, sk, st));
@@ -962,21 +1102,42 @@ static void rows_source(Source& S, const double* base, int r, int64_t ps, int64_
     S.col_stride = cs;
 }
 
+static int operator_pass(ttsk_ctx* ctx, int64_t nnz, const int64_t* d_idx_mu, int64_t n_mu, const double* d_val,
+                         const double* d_left, int rL, int64_t l_ps, int64_t l_cs, const double* d_right, int rR,
+                         int64_t r_ps, int64_t r_cs, double* d_out, cudaStream_t st) {
+    if (nnz == 0) return TTSK_OK;
+    const int64_t n_b = d_idx_mu ? n_mu : 1;
+    TTSK_TRY(ctx->ws_reserve(sortbufs_bytes(n_b, nnz) + 4096));
+    ctx->ws_reset();
+    SortBufs sb;
+    TTSK_TRY(carve_sortbufs(ctx, sb, n_b, nnz));
+    PassParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.nnz = nnz;
+    P.n_mu = n_b;
+    rows_source(P.A, d_left, rL, l_ps, l_cs);
+    rows_source(P.B, d_right, rR, r_ps, r_cs);
+    P.X.kind = SRC_NONE;
+    P.rA = d_left ? rL : 1;
+    P.rB = d_right ? rR : 1;
+    P.rX = 0;
+    P.psi = d_out;  // Omega is a Psi with a single slice
+    if (d_idx_mu) {
+        TTSK_TRY(sort_keys(ctx, nnz, (const long long*)d_idx_mu, n_b, sb, st));
+        P.keyid = sb.keyid;
+    }
+    P.val = d_val;
+    return launch_pass(ctx, P, false, st);
+}
+
 extern "C" int ttsk_sparse_omega(ttsk_ctx* ctx, int64_t nnz, const double* d_val, const double* d_left, int rL,
                                  int64_t l_ps, int64_t l_cs, const double* d_right, int rR, int64_t r_ps,
                                  int64_t r_cs, double* d_omega, void* stream) {
     TTSK_ARG(ctx != nullptr, "ctx is NULL");
     TTSK_ARG(nnz >= 0 && rL >= 1 && rR >= 1 && nnz < ((int64_t)1 << 31), "omega dims");
     TTSK_ARG(nnz == 0 || (d_val && d_left && d_right && d_omega), "NULL pointer");
-    PassParams P;
-    std::memset(&P, 0, sizeof(P));
-    P.d = 0; P.nnz = nnz; P.val = d_val; P.n_mu = 1; P.piece = 2048;
-    rows_source(P.A, d_left, rL, l_ps, l_cs);
-    rows_source(P.B, d_right, rR, r_ps, r_cs);
-    P.X.kind = SRC_NONE;
-    P.rA = rL; P.rB = rR; P.rX = 0;
-    P.psi = d_omega;  // a Psi with a single slice IS Omega
-    return launch_pass(ctx, P, false, (cudaStream_t)stream);
+    return operator_pass(ctx, nnz, nullptr, 1, d_val, d_left, rL, l_ps, l_cs, d_right, rR, r_ps, r_cs, d_omega,
+                         (cudaStream_t)stream);
 }
 
 extern "C" int ttsk_sparse_psi(ttsk_ctx* ctx, int64_t nnz, const int64_t* d_idx_mu, int64_t n_mu,
@@ -987,24 +1148,6 @@ extern "C" int ttsk_sparse_psi(ttsk_ctx* ctx, int64_t nnz, const int64_t* d_idx_
     TTSK_ARG(nnz >= 0 && n_mu >= 1 && nnz < ((int64_t)1 << 31) && n_mu < ((int64_t)1 << 31), "psi dims");
     TTSK_ARG(d_left != nullptr || d_right != nullptr, "sketch_psi_sparse needs at least one side (sparse_sketch.py:21-32)");
     TTSK_ARG(nnz == 0 || (d_val && d_idx_mu && d_psi), "NULL pointer");
-    if (nnz == 0) return TTSK_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    TTSK_TRY(ctx->ws_reserve(3 * (n_mu + 1) * 4 + 2 * nnz * 4 + 4096));
-    ctx->ws_reset();
-    int* d_hist = (int*)ctx->ws_alloc((n_mu + 1) * 4);
-    int* d_offs = (int*)ctx->ws_alloc((n_mu + 1) * 4);
-    int* d_cursor = (int*)ctx->ws_alloc((n_mu + 1) * 4);
-    int* d_perm = (int*)ctx->ws_alloc(nnz * 4);
-    int* d_skey = (int*)ctx->ws_alloc(nnz * 4);
-    TTSK_TRY(bucket_mode(ctx, (const long long*)d_idx_mu, nnz, n_mu, d_hist, d_offs, d_cursor, d_perm, d_skey, st));
-    PassParams P;
-    std::memset(&P, 0, sizeof(P));
-    P.d = 0; P.nnz = nnz; P.val = d_val; P.n_mu = n_mu; P.piece = 2048;
-    P.perm = d_perm; P.skey = d_skey;
-    rows_source(P.A, d_left, rL, l_ps, l_cs);
-    rows_source(P.B, d_right, rR, r_ps, r_cs);
-    P.X.kind = SRC_NONE;
-    P.rA = d_left ? rL : 1; P.rB = d_right ? rR : 1; P.rX = 0;
-    P.psi = d_psi;
-    return launch_pass(ctx, P, false, st);
+    return operator_pass(ctx, nnz, d_idx_mu, n_mu, d_val, d_left, rL, l_ps, l_cs, d_right, rR, r_ps, r_cs, d_psi,
+                         (cudaStream_t)stream);
 }
