@@ -70,6 +70,11 @@ int ttsk_lazy_gaussian(ttsk_ctx *ctx, const int64_t *d_idx, int64_t idx_row_stri
                        int64_t nnz, const int64_t *h_shape, int rank_min, int rank_max,
                        uint64_t seed, double *d_out, void *stream);
 
+/* Self-test of the straight-line FP64 division used inside the generator: counts operand
+ * pairs (n pseudo-random pairs from `seed`, magnitudes 2^-30..2^10 and zero numerators) whose
+ * quotient differs from CUDA's IEEE __ddiv_rn.  Must report 0.  Synchronous. */
+int ttsk_selftest_div(ttsk_ctx *ctx, int64_t n, uint64_t seed, uint64_t *h_mismatches);
+
 /* ---------------------------------------------------------------- DRM descriptors
  * A dimension-reduction map in USER orientation (bond mu = 0..d-2).
  * Replaces the state of tt_sketch/drm_base.py:14-63 (DRM), sparse_gaussian_drm.py:11-27 and

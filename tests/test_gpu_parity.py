@@ -50,6 +50,17 @@ def test_lazy_gaussian_bit_exact_vs_oracle_large(oracle_lib):
             assert bad == 0, (shape, k, bad)
 
 
+def test_straight_line_division_is_ieee():
+    """div_rn_safe (the branch-free division inside ndtri) == __ddiv_rn on 2e8 operand pairs."""
+    from ctypes import byref, c_uint64
+
+    from tt_sketch import _backend as be
+
+    bad = c_uint64(123)
+    be.check(be.lib().ttsk_selftest_div(be.ctx(), 200_000_000, 20240917, byref(bad)))
+    assert bad.value == 0
+
+
 def test_ndtri_tail_and_edge_uniforms(oracle_lib):
     """The deferred tail branch is exercised by every sketch; here the Gaussian rows of a sliced
     DRM must equal the same columns of the unsliced one bit-for-bit (reference

@@ -72,7 +72,38 @@ int gauss_table_launch(ttsk_ctx* ctx, int64_t rows, int rank_min, int rank, uint
     return gauss_rows_launch(ctx, gi, rows, rank_min, rank, seed, d_out, st);
 }
 
+// self-test: div_rn_safe vs __ddiv_rn on pseudo-random operands in the ranges ndtri uses
+__global__ void selftest_div_kernel(long long n, unsigned long long seed, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long h1 = hash64(seed + 2 * i), h2 = hash64(seed + 2 * i + 1);
+        const double ua = uniform_from_hash(h1), ub = uniform_from_hash(h2);
+        // numerators 2^-120..2^10, denominators 2^-30..2^10 (log-uniform), random signs, some exact zeros
+        const int ea = (int)((h1 >> 52) % 131) - 120, eb = (int)((h2 >> 52) % 41) - 30;
+        double a = ldexp(1.0 + ua, ea), b = ldexp(1.0 + ub, eb);
+        if (h1 >> 63) a = -a;
+        if (h2 >> 63) b = -b;
+        if ((i & 1023) == 0) a = 0.0;
+        const double want = __ddiv_rn(a, b), got = div_rn_safe(a, b);
+        if (__double_as_longlong(want) != __double_as_longlong(got)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace ttsk
+
+extern "C" int ttsk_selftest_div(ttsk_ctx* ctx, int64_t n, uint64_t seed, uint64_t* h_mismatches) {
+    TTSK_ARG(ctx != nullptr && h_mismatches != nullptr && n >= 0, "selftest_div");
+    unsigned long long* d = nullptr;
+    TTSK_CUDA(cudaMalloc((void**)&d, 8));
+    TTSK_CUDA(cudaMemset(d, 0, 8));
+    ttsk::selftest_div_kernel<<<ctx->sm_count * 8, 256>>>(n, seed, d);
+    TTSK_LAUNCHED(ctx);
+    TTSK_CUDA(cudaMemcpy(h_mismatches, d, 8, cudaMemcpyDeviceToHost));
+    TTSK_CUDA(cudaFree(d));
+    return TTSK_OK;
+}
 
 extern "C" int ttsk_lazy_gaussian(ttsk_ctx* ctx, const int64_t* d_idx, int64_t idx_row_stride, int k, int64_t nnz,
                                   const int64_t* h_shape, int rank_min, int rank_max, uint64_t seed, double* d_out,

@@ -22,6 +22,7 @@
 //     central branch runs without the tail's divergence.
 //   * edge bonds need no per-nonzero work:  Omega_0 = L_0^T Psi_0,  Omega_{d-2} = Psi_{d-1} R_{d-2}^T.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ttsk_common.cuh"
@@ -72,9 +73,12 @@ struct PassParams {
     // shared-memory plan (host computed)
     int pitchA, pitchB, pitchX;  // row pitch of each tile in doubles
     int bufsA, bufsB, bufsX;     // 1, or 2 for gathered (cp.async double-buffered) sources
-    unsigned long long magicA, magicB, magicX;  // ceil(2^32 / r) for the e -> (p, a) split
-    int queue_cap;
+    unsigned long long magicA, magicB, magicX;  // ceil(2^32 / r): thread id -> (row, column)
+    int rpiA, rpiB, rpiX;        // rows covered per sweep of the 256 threads (256 / r)
+    int queue_cap_w;             // tail-queue slots per warp
     int smem_bytes;
+    const int* offs;             // segment starts in the sorted order (n_mu + 1), or nullptr
+    long long work_items, item_len;
 };
 
 // ------------------------------------------------------------------ bucketing (counting sort)
@@ -259,43 +263,57 @@ __device__ __forceinline__ void gather_rows_async(const Source& S, double* __res
     }
 }
 
-// hash-seeded Gaussian source -> [TN][pitch] tile: central branch inline, tails queued
+// hash-seeded Gaussian source -> [TN][pitch] tile.
+// Thread t owns ONE column a = t % r (its salt lives in a register) and walks the rows
+// p = t / r, + rpi, + 2 rpi ... (rpi = 256 / r rows per sweep; 256 % r threads idle).  Two rows
+// are processed per iteration so two independent hash / Horner chains are in flight.  The
+// central branch of ndtri is evaluated for every lane without a branch (a diverged warp would
+// issue it anyway); lanes whose uniform falls in a tail keep the uniform in the tile and push
+// the slot on the warp's private queue, which the same warp drains densely afterwards.
 template <int TN>
-__device__ __forceinline__ void fill_gauss(const Source& S, unsigned long long magic, int src_id, double* __restrict__ tile,
-                                           int pitch, int len, const unsigned long long* __restrict__ s_flat,
-                                           const unsigned long long* __restrict__ s_salt, int* __restrict__ s_queue,
-                                           int* __restrict__ s_qcount) {
+__device__ __forceinline__ void fill_gauss(const Source& S, int rpi, unsigned long long magic, int src_id,
+                                           double* __restrict__ tile, int pitch, int len,
+                                           const unsigned long long* __restrict__ s_flat,
+                                           const unsigned long long* __restrict__ s_salt, int* __restrict__ wq,
+                                           int& wcount) {
     const int tid = threadIdx.x, lane = tid & 31;
-    const int total = S.r * len;
-    const int total_pad = (total + 31) & ~31;
-    for (int e0 = 0; e0 < total_pad; e0 += kPassThreads) {
-        const int e = e0 + tid;
-        bool tail = false;
-        int enc = 0;
-        if (e < total) {
-            const int p = (int)(((unsigned long long)(unsigned)e * magic) >> 32);
-            const int a = e - p * S.r;
-            const double u = uniform_from_hash(hash64(s_flat[p] + s_salt[a]));
-            const int cls = ndtri_class(u);
-            const int off = p * pitch + a;
-            if (cls == 0) {
-                tile[off] = ndtri_central(u);
-            } else {
-                tile[off] = u;
-                tail = true;
-                enc = (src_id << 28) | (cls << 26) | off;
-            }
-        }
-        if (e0 + (tid & ~31) < total) {  // warp-uniform: this warp still has items
-            const unsigned m = __ballot_sync(0xffffffffu, tail);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(s_qcount, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (tail) s_queue[base + __popc(m & ((1u << lane) - 1u))] = enc;
-            }
-        }
+    const unsigned lt = (1u << lane) - 1u;
+    const int prow = (int)(((unsigned long long)(unsigned)tid * magic) >> 32);
+    const int a = tid - prow * S.r;
+    const bool active = prow < rpi;
+    const unsigned long long salt = active ? s_salt[a] : 0ull;
+    const int sweeps = (len + rpi - 1) / rpi;
+    for (int it = 0; it < sweeps; it += 2) {
+        const int p0 = prow + it * rpi, p1 = p0 + rpi;
+        const bool v0 = active && p0 < len, v1 = active && p1 < len;
+        const double u0 = uniform_from_hash(hash64((v0 ? s_flat[p0] : 0ull) + salt));
+        const double u1 = uniform_from_hash(hash64((v1 ? s_flat[p1] : 0ull) + salt));
+        const double c0 = ndtri_central(u0), c1 = ndtri_central(u1);
+        const int k0 = ndtri_class(u0), k1 = ndtri_class(u1);
+        const bool t0 = v0 && k0 != 0, t1 = v1 && k1 != 0;
+        // rows that do not exist write to the spare row TN so both chains stay branch-free
+        const int off0 = (v0 ? p0 : TN) * pitch + (active ? a : 0), off1 = (v1 ? p1 : TN) * pitch + (active ? a : 0);
+        tile[off0] = t0 ? u0 : c0;
+        tile[off1] = t1 ? u1 : c1;
+        const unsigned m0 = __ballot_sync(0xffffffffu, t0);
+        if (t0) wq[wcount + __popc(m0 & lt)] = (src_id << 28) | (k0 << 26) | off0;
+        wcount += __popc(m0);
+        const unsigned m1 = __ballot_sync(0xffffffffu, t1);
+        if (t1) wq[wcount + __popc(m1 & lt)] = (src_id << 28) | (k1 << 26) | off1;
+        wcount += __popc(m1);
     }
+}
+
+// first sorted position >= x that starts a segment, if it is within `slack` of x; else x
+__device__ __forceinline__ long long snap_to_segment(const int* __restrict__ offs, long long n_mu, long long x,
+                                                     long long slack) {
+    long long lo = 0, hi = n_mu;  // offs[0..n_mu], offs[n_mu] = nnz
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if ((long long)offs[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    const long long b = offs[lo];
+    return (b - x <= slack) ? b : x;
 }
 
 // MI/NJ: 8x8 MMA tiles covering rA / max(rB, rX).  HAS_X: warps 4..7 accumulate
@@ -311,21 +329,23 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
     unsigned long long* s_fx = s_fb + kPiece;
     unsigned long long* s_salt = s_fx + kPiece;              // [3][64]
     double* At = reinterpret_cast<double*>(s_salt + 192);    // [bufsA][TN][PA]
-    double* Bt = At + P.bufsA * TN * PA;
-    double* Xt = Bt + P.bufsB * TN * PB;
-    int* s_key = reinterpret_cast<int*>(Xt + (HAS_X ? P.bufsX * TN * PX : 0));  // [kPiece]
-    int* s_queue = s_key + kPiece;                           // [queue_cap]
-    int* s_misc = s_queue + P.queue_cap;                     // qcount
+    constexpr int TR = TN + 1;  // one spare row per tile
+    double* Bt = At + P.bufsA * TR * PA;
+    double* Xt = Bt + P.bufsB * TR * PB;
+    int* s_key = reinterpret_cast<int*>(Xt + (HAS_X ? P.bufsX * TR * PX : 0));  // [kPiece]
+    int* s_queue = s_key + kPiece;                           // [kPassWarps][queue_cap_w]
+    long long* s_bounds = reinterpret_cast<long long*>(s_queue + kPassWarps * P.queue_cap_w + (P.queue_cap_w & 1));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const bool gatherA = (P.A.kind == SRC_ROWS || P.A.kind == SRC_TABLE);
     const bool gatherB = (P.B.kind == SRC_ROWS || P.B.kind == SRC_TABLE);
     const bool gatherX = HAS_X && (P.X.kind == SRC_ROWS || P.X.kind == SRC_TABLE);
+    int* wq = s_queue + warp * P.queue_cap_w;
 
     load_logtab(s_tab);
     {
-        const int tile_doubles = P.bufsA * TN * PA + P.bufsB * TN * PB + (HAS_X ? P.bufsX * TN * PX : 0);
+        const int tile_doubles = P.bufsA * TR * PA + P.bufsB * TR * PB + (HAS_X ? P.bufsX * TR * PX : 0);
         for (int i = tid; i < tile_doubles; i += kPassThreads) At[i] = 0.0;
     }
     if (P.A.kind == SRC_GAUSS)
@@ -367,119 +387,138 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
         if (!omega_role) flush(P.psi + key * P.rB, (long long)P.n_mu * P.rB, P.rB);
     };
 
-    const long long n_pieces = (P.nnz + kPiece - 1) / kPiece;
-    for (long long piece = blockIdx.x; piece < n_pieces; piece += gridDim.x) {
-        const long long s = piece * kPiece;
-        const int n_piece = (int)((s + kPiece < P.nnz) ? kPiece : P.nnz - s);
-        __syncthreads();  // previous piece fully consumed (tiles, records, queue)
-        // ---- stage the piece: stream the sorted (key, id) words, gather value and index rows
-        for (int i = tid; i < kPiece; i += kPassThreads) {
-            const bool in = i < n_piece;
-            long long id = s + i;
-            int key = in ? 0 : -1;
-            if (in && P.keyid) {
-                const unsigned long long w = P.keyid[s + i];
-                id = (long long)(w & 0xffffffffull);
-                key = (int)(w >> 32);
-            }
-            s_key[i] = key;
-            s_val[i] = in ? P.val[id] : 0.0;
-            if (P.A.kind != SRC_NONE) s_fa[i] = in ? fold_flat(P.A, P.idx, id) : 0ull;
-            if (P.B.kind != SRC_NONE) s_fb[i] = in ? fold_flat(P.B, P.idx, id) : 0ull;
-            if (HAS_X) s_fx[i] = in ? fold_flat(P.X, P.idx, id) : 0ull;
-        }
-        if (tid == 0) s_misc[0] = 0;
+    // ---- work items: contiguous ranges of the sorted order, cut at segment boundaries where
+    // one is near (so a slice of Psi is flushed by one CTA, once), inside long segments otherwise
+    for (long long item = blockIdx.x; item < P.work_items; item += gridDim.x) {
         __syncthreads();
-        long long cur_key = -1;
-        int c = 0, buf = 0;
-        // gather of the first tile
-        {
-            const int rows = (n_piece < TN) ? n_piece : TN;
-            if (gatherA) gather_rows_async<TN>(P.A, At, PA, s_fa, rows);
-            if (gatherB) gather_rows_async<TN>(P.B, Bt, PB, s_fb, rows);
-            if (gatherX) gather_rows_async<TN>(P.X, Xt, PX, s_fx, rows);
-            cp_async_commit();
+        if (tid == 0) {
+            long long lo = item * P.item_len, hi = (item + 1) * P.item_len;
+            if (hi > P.nnz || item == P.work_items - 1) hi = P.nnz;
+            if (P.offs) {
+                if (item > 0) lo = snap_to_segment(P.offs, P.n_mu, lo, P.item_len / 2);
+                if (hi < P.nnz) hi = snap_to_segment(P.offs, P.n_mu, hi, P.item_len / 2);
+            }
+            s_bounds[0] = lo;
+            s_bounds[1] = hi;
         }
-        while (c < n_piece) {
-            // ---- run of equal keys starting at c, at most TN long (every warp computes it)
-            int len = 0;
-            const int key0 = s_key[c];
-            {
-                bool open = true;
+        __syncthreads();
+        const long long item_lo = s_bounds[0], item_hi = s_bounds[1];
+        long long cur_key = -1;
+        // (key, id) words of the next piece are prefetched while the current piece is processed
+        unsigned long long w_next[kPiece / kPassThreads];
 #pragma unroll
-                for (int t = 0; t < TN / 32; t++) {
-                    const int pos = c + t * 32 + lane;
-                    const bool same = (pos < n_piece) && (s_key[pos] == key0);
-                    const unsigned m = __ballot_sync(0xffffffffu, same);
-                    if (open) {
-                        if (m == 0xffffffffu) len += 32;
-                        else { len += __ffs(~m) - 1; open = false; }
+        for (int u = 0; u < kPiece / kPassThreads; u++) {
+            const long long pos = item_lo + u * kPassThreads + tid;
+            w_next[u] = (P.keyid && pos < item_hi) ? P.keyid[pos] : 0ull;
+        }
+        for (long long s = item_lo; s < item_hi; s += kPiece) {
+            const int n_piece = (int)((s + kPiece < item_hi) ? kPiece : item_hi - s);
+            __syncthreads();  // previous piece fully consumed (tiles, staged records, queues)
+            // ---- stage the piece: gather value and index rows of every nonzero, fold flat indices
+#pragma unroll
+            for (int u = 0; u < kPiece / kPassThreads; u++) {
+                const int i = u * kPassThreads + tid;
+                const bool in = i < n_piece;
+                long long id = s + i;
+                int key = in ? 0 : -1;
+                if (in && P.keyid) {
+                    id = (long long)(w_next[u] & 0xffffffffull);
+                    key = (int)(w_next[u] >> 32);
+                }
+                const long long npos = s + kPiece + i;
+                w_next[u] = (P.keyid && npos < item_hi) ? P.keyid[npos] : 0ull;
+                s_key[i] = key;
+                s_val[i] = in ? P.val[id] : 0.0;
+                if (P.A.kind != SRC_NONE) s_fa[i] = in ? fold_flat(P.A, P.idx, id) : 0ull;
+                if (P.B.kind != SRC_NONE) s_fb[i] = in ? fold_flat(P.B, P.idx, id) : 0ull;
+                if (HAS_X) s_fx[i] = in ? fold_flat(P.X, P.idx, id) : 0ull;
+            }
+            __syncthreads();
+            int c = 0, buf = 0;
+            {   // gather of the first tile
+                const int rows = (n_piece < TN) ? n_piece : TN;
+                if (gatherA) gather_rows_async<TN>(P.A, At, PA, s_fa, rows);
+                if (gatherB) gather_rows_async<TN>(P.B, Bt, PB, s_fb, rows);
+                if (gatherX) gather_rows_async<TN>(P.X, Xt, PX, s_fx, rows);
+                cp_async_commit();
+            }
+            while (c < n_piece) {
+                // ---- run of equal keys starting at c, at most TN long (every warp computes it)
+                int len = 0;
+                const int key0 = s_key[c];
+                {
+                    bool open = true;
+#pragma unroll
+                    for (int t = 0; t < TN / 32; t++) {
+                        const int pos = c + t * 32 + lane;
+                        const bool same = (pos < n_piece) && (s_key[pos] == key0);
+                        const unsigned m = __ballot_sync(0xffffffffu, same);
+                        if (open) {
+                            if (m == 0xffffffffu) len += 32;
+                            else { len += __ffs(~m) - 1; open = false; }
+                        }
                     }
                 }
-            }
-            const int next_c = c + len;
-            // ---- prefetch the gathered rows of the NEXT tile, then wait for this tile's
-            if (next_c < n_piece) {
-                const int rows = (n_piece - next_c < TN) ? n_piece - next_c : TN;
-                const int nb = buf ^ 1;
-                if (gatherA) gather_rows_async<TN>(P.A, At + nb * TN * PA, PA, s_fa + next_c, rows);
-                if (gatherB) gather_rows_async<TN>(P.B, Bt + nb * TN * PB, PB, s_fb + next_c, rows);
-                if (gatherX) gather_rows_async<TN>(P.X, Xt + nb * TN * PX, PX, s_fx + next_c, rows);
-            }
-            cp_async_commit();
-            cp_async_wait<1>();
-            if ((long long)key0 != cur_key) {
-                if (cur_key >= 0) flush_psi(cur_key);
-                cur_key = key0;
-            }
-            double* At_c = At + (P.bufsA == 2 ? buf * TN * PA : 0);
-            double* Bt_c = Bt + (P.bufsB == 2 ? buf * TN * PB : 0);
-            double* Xt_c = Xt + (HAS_X && P.bufsX == 2 ? buf * TN * PX : 0);
-            // ---- on-the-fly sources (central branch inline, tails queued)
-            if (P.A.kind == SRC_GAUSS)
-                fill_gauss<TN>(P.A, P.magicA, 0, At_c, PA, len, s_fa + c, s_salt, s_queue, &s_misc[0]);
-            else if (P.A.kind == SRC_NONE && tid < TN) At_c[tid * PA] = 1.0;
-            if (P.B.kind == SRC_GAUSS)
-                fill_gauss<TN>(P.B, P.magicB, 1, Bt_c, PB, len, s_fb + c, s_salt + 64, s_queue, &s_misc[0]);
-            else if (P.B.kind == SRC_NONE && tid < TN) Bt_c[tid * PB] = 1.0;
-            if (HAS_X && P.X.kind == SRC_GAUSS)
-                fill_gauss<TN>(P.X, P.magicX, 2, Xt_c, PX, len, s_fx + c, s_salt + 128, s_queue, &s_misc[0]);
-            __syncthreads();
-            // ---- deferred tails, dense over the queue
-            {
-                const int nq = s_misc[0];
-                for (int qi = tid; qi < nq; qi += kPassThreads) {
-                    const int enc = s_queue[qi];
+                const int next_c = c + len;
+                // ---- prefetch the gathered rows of the NEXT tile, then wait for this tile's
+                if (next_c < n_piece) {
+                    const int rows = (n_piece - next_c < TN) ? n_piece - next_c : TN;
+                    const int nb = buf ^ 1;
+                    if (gatherA) gather_rows_async<TN>(P.A, At + nb * TR * PA, PA, s_fa + next_c, rows);
+                    if (gatherB) gather_rows_async<TN>(P.B, Bt + nb * TR * PB, PB, s_fb + next_c, rows);
+                    if (gatherX) gather_rows_async<TN>(P.X, Xt + nb * TR * PX, PX, s_fx + next_c, rows);
+                }
+                cp_async_commit();
+                cp_async_wait<1>();
+                if ((long long)key0 != cur_key) {
+                    if (cur_key >= 0) flush_psi(cur_key);
+                    cur_key = key0;
+                }
+                double* At_c = At + (P.bufsA == 2 ? buf * TR * PA : 0);
+                double* Bt_c = Bt + (P.bufsB == 2 ? buf * TR * PB : 0);
+                double* Xt_c = Xt + (HAS_X && P.bufsX == 2 ? buf * TR * PX : 0);
+                // ---- on-the-fly sources, then this warp's deferred tails
+                int wcount = 0;
+                if (P.A.kind == SRC_GAUSS)
+                    fill_gauss<TN>(P.A, P.rpiA, P.magicA, 0, At_c, PA, len, s_fa + c, s_salt, wq, wcount);
+                else if (P.A.kind == SRC_NONE && tid < TN) At_c[tid * PA] = 1.0;
+                if (P.B.kind == SRC_GAUSS)
+                    fill_gauss<TN>(P.B, P.rpiB, P.magicB, 1, Bt_c, PB, len, s_fb + c, s_salt + 64, wq, wcount);
+                else if (P.B.kind == SRC_NONE && tid < TN) Bt_c[tid * PB] = 1.0;
+                if (HAS_X && P.X.kind == SRC_GAUSS)
+                    fill_gauss<TN>(P.X, P.rpiX, P.magicX, 2, Xt_c, PX, len, s_fx + c, s_salt + 128, wq, wcount);
+                __syncwarp();
+                for (int qi = lane; qi < wcount; qi += 32) {
+                    const int enc = wq[qi];
                     const int src = enc >> 28, cls = (enc >> 26) & 3, off = enc & 0x3ffffff;
                     double* tile = src == 0 ? At_c : (src == 1 ? Bt_c : Xt_c);
                     tile[off] = ndtri_tail(tile[off], cls, s_tab);
                 }
-            }
-            __syncthreads();
-            if (tid == 0) s_misc[0] = 0;
-            // ---- accumulate: k-chunks of 4 nonzeros; A fragment scaled by the value
-            {
-                const double* Rt = omega_role ? Xt_c : Bt_c;
-                const int PR = omega_role ? PX : PB;
-                for (int ch = role_rank; ch * 4 < len; ch += role_warps) {
-                    const int p0 = ch * 4 + q;
-                    const double v = (p0 < len) ? s_val[c + p0] : 0.0;
-                    double a[MI], b[NJ];
+                __syncthreads();
+                // ---- accumulate: k-chunks of 4 nonzeros; A fragment scaled by the value
+                {
+                    const double* Rt = omega_role ? Xt_c : Bt_c;
+                    const int PR = omega_role ? PX : PB;
+                    for (int ch = role_rank; ch * 4 < len; ch += role_warps) {
+                        const int p0 = ch * 4 + q;
+                        const double v = (p0 < len) ? s_val[c + p0] : 0.0;
+                        double a[MI], b[NJ];
 #pragma unroll
-                    for (int i = 0; i < MI; i++) a[i] = At_c[p0 * PA + 8 * i + g] * v;
+                        for (int i = 0; i < MI; i++) a[i] = At_c[p0 * PA + 8 * i + g] * v;
 #pragma unroll
-                    for (int j = 0; j < NJ; j++) b[j] = Rt[p0 * PR + 8 * j + g];
+                        for (int j = 0; j < NJ; j++) b[j] = Rt[p0 * PR + 8 * j + g];
 #pragma unroll
-                    for (int i = 0; i < MI; i++)
+                        for (int i = 0; i < MI; i++)
 #pragma unroll
-                        for (int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                            for (int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    }
                 }
+                __syncthreads();
+                c = next_c;
+                buf ^= 1;
             }
-            __syncthreads();
-            c = next_c;
-            buf ^= 1;
+            cp_async_wait<0>();
         }
-        cp_async_wait<0>();
         if (cur_key >= 0) flush_psi(cur_key);
     }
     if (omega_role) flush(P.omega, P.rX, P.rX);
@@ -499,15 +538,18 @@ static int launch_pass_t(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     P.magicA = magic(P.A.r > 0 ? P.A.r : 1);
     P.magicB = magic(P.B.r > 0 ? P.B.r : 1);
     P.magicX = magic(P.X.r > 0 ? P.X.r : 1);
-    int otf_cols = 0;
-    if (P.A.kind == SRC_GAUSS) otf_cols += P.A.r;
-    if (P.B.kind == SRC_GAUSS) otf_cols += P.B.r;
-    if (HAS_X && P.X.kind == SRC_GAUSS) otf_cols += P.X.r;
-    P.queue_cap = otf_cols * TN + 32;
-    const size_t tile_doubles = (size_t)P.bufsA * TN * P.pitchA + (size_t)P.bufsB * TN * P.pitchB +
-                                (size_t)P.bufsX * TN * P.pitchX;
+    P.rpiA = kPassThreads / (P.A.r > 0 ? P.A.r : 1);
+    P.rpiB = kPassThreads / (P.B.r > 0 ? P.B.r : 1);
+    P.rpiX = kPassThreads / (P.X.r > 0 ? P.X.r : 1);
+    int per_lane = 0;  // worst-case queued tails per lane and tile
+    if (P.A.kind == SRC_GAUSS) per_lane += (TN + P.rpiA - 1) / P.rpiA + 1;
+    if (P.B.kind == SRC_GAUSS) per_lane += (TN + P.rpiB - 1) / P.rpiB + 1;
+    if (HAS_X && P.X.kind == SRC_GAUSS) per_lane += (TN + P.rpiX - 1) / P.rpiX + 1;
+    P.queue_cap_w = 32 * per_lane + 32;
+    const size_t tile_doubles = (size_t)P.bufsA * (TN + 1) * P.pitchA + (size_t)P.bufsB * (TN + 1) * P.pitchB +
+                                (size_t)P.bufsX * (TN + 1) * P.pitchX;
     const size_t smem = 128 * 16 + (size_t)kPiece * 8 * 4 + 192 * 8 + tile_doubles * 8 + (size_t)kPiece * 4 +
-                        (size_t)P.queue_cap * 4 + 64;
+                        (size_t)(kPassWarps * P.queue_cap_w + 2) * 4 + 64;
     P.smem_bytes = (int)smem;
     TTSK_ARG(smem <= 227 * 1024, "sparse pass: shared-memory plan exceeds 227 KB (ranks too large)");
     TTSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -515,10 +557,19 @@ static int launch_pass_t(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     int per_sm = 1;
     TTSK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPassThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    const long long n_pieces = (P.nnz + kPiece - 1) / kPiece;
     long long grid = (long long)ctx->sm_count * per_sm;
-    if (grid > n_pieces) grid = n_pieces;
+    // ~8 work items per CTA for balance, none shorter than a few pieces
+    long long items = grid * 8;
+    const long long min_len = 8 * kPiece;
+    if (items * min_len > P.nnz) items = (P.nnz + min_len - 1) / min_len;
+    if (items < 1) items = 1;
+    P.work_items = items;
+    P.item_len = (P.nnz + items - 1) / items;
+    if (grid > items) grid = items;
     if (grid < 1) grid = 1;
+    if (getenv("TTSK_DEBUG"))
+        fprintf(stderr, "[ttsk] pass MI=%d NJ=%d X=%d TN=%d smem=%zu ctas/sm=%d grid=%lld items=%lld\n", MI, NJ, (int)HAS_X, TN,
+                smem, per_sm, grid, items);
     kern<<<(unsigned)grid, kPassThreads, smem, st>>>(P);
     TTSK_LAUNCHED(ctx);
     return TTSK_OK;
@@ -529,7 +580,9 @@ static int launch_pass_x(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     const int mi = (P.rA + 7) / 8;
     const int nj = (std::max(P.rB, HAS_X ? P.rX : 1) + 7) / 8;
     TTSK_ARG(mi <= 8 && nj <= 8, "sparse pass: DRM rank above 64 is not supported by the fused kernel");
-#define TTSK_PASS(MI_, NJ_) return launch_pass_t<MI_, NJ_, HAS_X, 64>(ctx, P, st)
+#define TTSK_PASS(MI_, NJ_)                                                            \
+    return (tn == 32) ? launch_pass_t<MI_, NJ_, HAS_X, 32>(ctx, P, st) : launch_pass_t<MI_, NJ_, HAS_X, 64>(ctx, P, st)
+    static const int tn = getenv("TTSK_TN") ? atoi(getenv("TTSK_TN")) : 64;
     const int MIr = mi <= 1 ? 1 : (mi <= 3 ? 3 : (mi <= 5 ? 5 : 8));
     const int NJr = nj <= 1 ? 1 : (nj <= 3 ? 3 : (nj <= 5 ? 5 : 8));
     switch (MIr * 10 + NJr) {
@@ -769,6 +822,7 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
         }
         TTSK_TRY(sort_keys(ctx, nnz, idx_rows[mu], shape[mu], sb, st));
         P.keyid = sb.keyid;
+        P.offs = sb.offs;
         for (int m = 0; m < d; m++) P.idx[m] = idx_rows[m];
         P.val = d_val;
         P.psi = out + lay.psi_off[mu];
@@ -1125,6 +1179,7 @@ static int operator_pass(ttsk_ctx* ctx, int64_t nnz, const int64_t* d_idx_mu, in
     if (d_idx_mu) {
         TTSK_TRY(sort_keys(ctx, nnz, (const long long*)d_idx_mu, n_b, sb, st));
         P.keyid = sb.keyid;
+        P.offs = sb.offs;
     }
     P.val = d_val;
     return launch_pass(ctx, P, false, st);
