@@ -53,6 +53,10 @@ struct Source {
 // and gathers the value / index rows of each nonzero itself: those random 8-byte reads run on
 // the otherwise idle memory pipes of an FP64-bound kernel instead of in a separate
 // bandwidth-bound sort kernel.
+struct ScatterIdx {
+    const long long* idx[TTSK_MAX_ORDER];
+};
+
 struct ScatterParams {
     long long nnz;
     const long long* key_idx;
@@ -64,8 +68,9 @@ struct PassParams {
     long long nnz;
     long long n_mu;
     const unsigned long long* keyid;  // sorted (key << 32 | id); nullptr: identity order, key 0
-    const long long* idx[TTSK_MAX_ORDER];
-    const double* val;
+    const unsigned* recs;    // packed records [val(2 words) | int32 idx[d] | pad], rec_words each; or nullptr
+    int rec_words;
+    const double* val;       // used when recs == nullptr (operator-level passes need no indices)
     Source A, B, X;
     int rA, rB, rX;  // logical tile widths (1 for SRC_NONE)
     double* psi;     // (rA, n_mu, rB)
@@ -79,6 +84,7 @@ struct PassParams {
     int smem_bytes;
     const int* offs;             // segment starts in the sorted order (n_mu + 1), or nullptr
     long long work_items, item_len;
+    int debug;  // ablation switches for profiling (TTSK_ABLATE): 1 no ndtri, 2 no MMA, 4 no gathers, 8 no flush, 16 no tails
 };
 
 // ------------------------------------------------------------------ bucketing (counting sort)
@@ -145,13 +151,37 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ hist
     if (threadIdx.x == 0) offs[n] = s_carry;
 }
 
-__device__ __forceinline__ unsigned long long fold_flat(const Source& f, const long long* const* idx,
-                                                        long long p) {
-    if (f.kind == SRC_ROWS) return (unsigned long long)p;
+// flat index of one source from a packed record (int32 indices start at word 2); the record is a
+// single 32-byte sector, so after the value has been read these loads hit L1
+__device__ __forceinline__ unsigned long long fold_flat(const Source& f, const unsigned* __restrict__ rec,
+                                                        long long id) {
+    if (f.kind == SRC_ROWS) return (unsigned long long)id;
     unsigned long long flat = 0;
     for (int i = 0; i < f.k; i++)
-        flat += (unsigned long long)idx[f.modes[i]][p] * (unsigned long long)f.strides[i];
+        flat += (unsigned long long)rec[2 + f.modes[i]] * (unsigned long long)f.strides[i];
     return flat;
+}
+
+// Pack the chunk's COO arrays (SoA, int64 indices) into one sector-sized record per nonzero so a
+// mode pass fetches a nonzero with ONE random 32-byte access instead of d+1 of them.
+__global__ void pack_records_kernel(int d, long long nnz, ScatterIdx rows, const double* __restrict__ val,
+                                    unsigned* __restrict__ recs, int rec_words) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nnz;
+         p += (long long)gridDim.x * blockDim.x) {
+        unsigned* r = recs + p * rec_words;
+        const unsigned long long v = (unsigned long long)__double_as_longlong(val[p]);
+        unsigned w[8];
+        w[0] = (unsigned)v; w[1] = (unsigned)(v >> 32);
+        for (int base = 0; base < rec_words; base += 8) {
+#pragma unroll
+            for (int j = (base == 0 ? 2 : 0); j < 8; j++) {
+                const int m = base + j - 2;
+                w[j] = (m < d) ? (unsigned)rows.idx[m][p] : 0u;
+            }
+            reinterpret_cast<uint4*>(r + base)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4*>(r + base)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    }
 }
 
 __global__ void scatter_kernel(const ScatterParams S) {
@@ -275,7 +305,7 @@ __device__ __forceinline__ void fill_gauss(const Source& S, int rpi, unsigned lo
                                            double* __restrict__ tile, int pitch, int len,
                                            const unsigned long long* __restrict__ s_flat,
                                            const unsigned long long* __restrict__ s_salt, int* __restrict__ wq,
-                                           int& wcount) {
+                                           int& wcount, int debug) {
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int prow = (int)(((unsigned long long)(unsigned)tid * magic) >> 32);
@@ -288,8 +318,8 @@ __device__ __forceinline__ void fill_gauss(const Source& S, int rpi, unsigned lo
         const bool v0 = active && p0 < len, v1 = active && p1 < len;
         const double u0 = uniform_from_hash(hash64((v0 ? s_flat[p0] : 0ull) + salt));
         const double u1 = uniform_from_hash(hash64((v1 ? s_flat[p1] : 0ull) + salt));
-        const double c0 = ndtri_central(u0), c1 = ndtri_central(u1);
-        const int k0 = ndtri_class(u0), k1 = ndtri_class(u1);
+        const double c0 = (debug & 1) ? u0 : ndtri_central(u0), c1 = (debug & 1) ? u1 : ndtri_central(u1);
+        const int k0 = (debug & 17) ? 0 : ndtri_class(u0), k1 = (debug & 17) ? 0 : ndtri_class(u1);
         const bool t0 = v0 && k0 != 0, t1 = v1 && k1 != 0;
         // rows that do not exist write to the spare row TN so both chains stay branch-free
         const int off0 = (v0 ? p0 : TN) * pitch + (active ? a : 0), off1 = (v1 ? p1 : TN) * pitch + (active ? a : 0);
@@ -338,9 +368,9 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const bool gatherA = (P.A.kind == SRC_ROWS || P.A.kind == SRC_TABLE);
-    const bool gatherB = (P.B.kind == SRC_ROWS || P.B.kind == SRC_TABLE);
-    const bool gatherX = HAS_X && (P.X.kind == SRC_ROWS || P.X.kind == SRC_TABLE);
+    const bool gatherA = !(P.debug & 4) && (P.A.kind == SRC_ROWS || P.A.kind == SRC_TABLE);
+    const bool gatherB = !(P.debug & 4) && (P.B.kind == SRC_ROWS || P.B.kind == SRC_TABLE);
+    const bool gatherX = !(P.debug & 4) && HAS_X && (P.X.kind == SRC_ROWS || P.X.kind == SRC_TABLE);
     int* wq = s_queue + warp * P.queue_cap_w;
 
     load_logtab(s_tab);
@@ -375,7 +405,7 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
 #pragma unroll
             for (int j = 0; j < NJ; j++) {
                 const int row = 8 * i + g, col = 8 * j + 2 * q;
-                if (row < P.rA) {
+                if (row < P.rA && !(P.debug & 8)) {
                     double* dst = dst_base + (long long)row * row_pitch + col;
                     if (col < ncols && acc[i][j][0] != 0.0) atomicAdd(dst, acc[i][j][0]);
                     if (col + 1 < ncols && acc[i][j][1] != 0.0) atomicAdd(dst + 1, acc[i][j][1]);
@@ -428,10 +458,11 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
                 const long long npos = s + kPiece + i;
                 w_next[u] = (P.keyid && npos < item_hi) ? P.keyid[npos] : 0ull;
                 s_key[i] = key;
-                s_val[i] = in ? P.val[id] : 0.0;
-                if (P.A.kind != SRC_NONE) s_fa[i] = in ? fold_flat(P.A, P.idx, id) : 0ull;
-                if (P.B.kind != SRC_NONE) s_fb[i] = in ? fold_flat(P.B, P.idx, id) : 0ull;
-                if (HAS_X) s_fx[i] = in ? fold_flat(P.X, P.idx, id) : 0ull;
+                const unsigned* rec = P.recs ? P.recs + id * P.rec_words : nullptr;
+                s_val[i] = in ? (rec ? *reinterpret_cast<const double*>(rec) : P.val[id]) : 0.0;
+                if (P.A.kind != SRC_NONE) s_fa[i] = in ? fold_flat(P.A, rec, id) : 0ull;
+                if (P.B.kind != SRC_NONE) s_fb[i] = in ? fold_flat(P.B, rec, id) : 0ull;
+                if (HAS_X) s_fx[i] = in ? fold_flat(P.X, rec, id) : 0ull;
             }
             __syncthreads();
             int c = 0, buf = 0;
@@ -480,13 +511,13 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
                 // ---- on-the-fly sources, then this warp's deferred tails
                 int wcount = 0;
                 if (P.A.kind == SRC_GAUSS)
-                    fill_gauss<TN>(P.A, P.rpiA, P.magicA, 0, At_c, PA, len, s_fa + c, s_salt, wq, wcount);
+                    fill_gauss<TN>(P.A, P.rpiA, P.magicA, 0, At_c, PA, len, s_fa + c, s_salt, wq, wcount, P.debug);
                 else if (P.A.kind == SRC_NONE && tid < TN) At_c[tid * PA] = 1.0;
                 if (P.B.kind == SRC_GAUSS)
-                    fill_gauss<TN>(P.B, P.rpiB, P.magicB, 1, Bt_c, PB, len, s_fb + c, s_salt + 64, wq, wcount);
+                    fill_gauss<TN>(P.B, P.rpiB, P.magicB, 1, Bt_c, PB, len, s_fb + c, s_salt + 64, wq, wcount, P.debug);
                 else if (P.B.kind == SRC_NONE && tid < TN) Bt_c[tid * PB] = 1.0;
                 if (HAS_X && P.X.kind == SRC_GAUSS)
-                    fill_gauss<TN>(P.X, P.rpiX, P.magicX, 2, Xt_c, PX, len, s_fx + c, s_salt + 128, wq, wcount);
+                    fill_gauss<TN>(P.X, P.rpiX, P.magicX, 2, Xt_c, PX, len, s_fx + c, s_salt + 128, wq, wcount, P.debug);
                 __syncwarp();
                 for (int qi = lane; qi < wcount; qi += 32) {
                     const int enc = wq[qi];
@@ -499,7 +530,7 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
                 {
                     const double* Rt = omega_role ? Xt_c : Bt_c;
                     const int PR = omega_role ? PX : PB;
-                    for (int ch = role_rank; ch * 4 < len; ch += role_warps) {
+                    for (int ch = role_rank; ch * 4 < len && !(P.debug & 2); ch += role_warps) {
                         const int p0 = ch * 4 + q;
                         const double v = (p0 < len) ? s_val[c + p0] : 0.0;
                         double a[MI], b[NJ];
@@ -563,6 +594,7 @@ static int launch_pass_t(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     const long long min_len = 8 * kPiece;
     if (items * min_len > P.nnz) items = (P.nnz + min_len - 1) / min_len;
     if (items < 1) items = 1;
+    P.debug = getenv("TTSK_ABLATE") ? atoi(getenv("TTSK_ABLATE")) : 0;
     P.work_items = items;
     P.item_len = (P.nnz + items - 1) / items;
     if (grid > items) grid = items;
@@ -617,11 +649,21 @@ static int launch_pass(ttsk_ctx* ctx, PassParams& P, bool has_x, cudaStream_t st
 struct SortBufs {
     int* hist; int* offs; int* cursor;
     unsigned long long* keyid;
+    unsigned* recs;
+    int rec_words;
 };
-static int64_t sortbufs_bytes(int64_t n_max, int64_t chunk) {
-    return 3 * align_up((n_max + 1) * 4, 256) + align_up(chunk * 8, 256) + 2048;
+static int rec_words_for(int d) { return d <= 0 ? 0 : (int)align_up(2 + d, 8); }
+static int64_t sortbufs_bytes(int64_t n_max, int64_t chunk, int d) {
+    return 3 * align_up((n_max + 1) * 4, 256) + align_up(chunk * 8, 256) + align_up(chunk * 4 * rec_words_for(d), 256) +
+           2048;
 }
-static int carve_sortbufs(ttsk_ctx* ctx, SortBufs& sb, int64_t n_max, int64_t chunk) {
+static int carve_sortbufs(ttsk_ctx* ctx, SortBufs& sb, int64_t n_max, int64_t chunk, int d) {
+    sb.rec_words = rec_words_for(d);
+    sb.recs = sb.rec_words ? (unsigned*)ctx->ws_alloc(chunk * 4 * sb.rec_words) : nullptr;
+    if (sb.rec_words && !sb.recs) {
+        set_error("workspace carve failed (packed records)");
+        return TTSK_E_NOMEM;
+    }
     sb.hist = (int*)ctx->ws_alloc((n_max + 1) * 4);
     sb.offs = (int*)ctx->ws_alloc((n_max + 1) * 4);
     sb.cursor = (int*)ctx->ws_alloc((n_max + 1) * 4);
@@ -777,7 +819,7 @@ struct SparsePlan {
 };
 
 static int64_t chunk_bytes_per_nnz(int d, const ttsk_drm* left, const ttsk_drm* right) {
-    int64_t b = 8;  // sorted (key, id) words
+    int64_t b = 8 + 4 * rec_words_for(d);  // sorted (key, id) words + packed records
     if (left->kind == TTSK_DRM_TT)
         for (int k = 0; k < d - 1; k++) b += 8LL * left->core_r1[k];
     if (right->kind == TTSK_DRM_TT)
@@ -803,6 +845,14 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
                                 shape[d - 1 - k], right->core_r1[k], pl.right.chain[k], st));
     const long long* idx_rows[TTSK_MAX_ORDER];
     for (int m = 0; m < d; m++) idx_rows[m] = (const long long*)(d_idx + m * idx_row_stride);
+    {
+        ScatterIdx rows;
+        for (int m = 0; m < TTSK_MAX_ORDER; m++) rows.idx[m] = m < d ? idx_rows[m] : nullptr;
+        long long blocks = (nnz + 255) / 256;
+        if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
+        pack_records_kernel<<<(unsigned)blocks, 256, 0, st>>>(d, nnz, rows, d_val, sb.recs, sb.rec_words);
+        TTSK_LAUNCHED(ctx);
+    }
     for (int mu = 0; mu < d; mu++) {
         PassParams P;
         std::memset(&P, 0, sizeof(P));
@@ -823,7 +873,8 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
         TTSK_TRY(sort_keys(ctx, nnz, idx_rows[mu], shape[mu], sb, st));
         P.keyid = sb.keyid;
         P.offs = sb.offs;
-        for (int m = 0; m < d; m++) P.idx[m] = idx_rows[m];
+        P.recs = sb.recs;
+        P.rec_words = sb.rec_words;
         P.val = d_val;
         P.psi = out + lay.psi_off[mu];
         if (ctx->timing) {
@@ -905,7 +956,7 @@ static int64_t plan_workspace_bytes(int d, const int64_t* shape, int64_t nnz_tot
     int64_t bytes = 0;
     auto add = [&](int64_t b) { bytes = align_up(bytes, 256) + b; };
     add(sketch_elems * 8);                  // temp sketch when accumulating
-    add(sortbufs_bytes(n_max, chunk));      // hist/offs/cursor + sorted records
+    add(sortbufs_bytes(n_max, chunk, d));   // hist/offs/cursor + sorted (key, id) words + packed records
     const int64_t table_rows_cap = std::max<int64_t>(nnz_total / 4, 1);
     for (int side = 0; side < 2; side++) {
         const ttsk_drm* drm = side == 0 ? left : right;
@@ -1003,7 +1054,7 @@ extern "C" int ttsk_sparse_sketch(ttsk_ctx* ctx, int d, const int64_t* h_shape, 
     int64_t n_max = 0;
     for (int mu = 0; mu < d; mu++) n_max = std::max<int64_t>(n_max, h_shape[mu]);
     SortBufs sb;
-    TTSK_TRY(carve_sortbufs(ctx, sb, n_max, chunk));
+    TTSK_TRY(carve_sortbufs(ctx, sb, n_max, chunk, d));
     if (!tmp) {
         set_error("workspace carve failed");
         return TTSK_E_NOMEM;
@@ -1072,7 +1123,7 @@ static int sparse_sketch_from_host(ttsk_ctx* ctx, int d, const int64_t* h_shape,
     int64_t n_max = 0;
     for (int mu = 0; mu < d; mu++) n_max = std::max<int64_t>(n_max, h_shape[mu]);
     SortBufs sb;
-    TTSK_TRY(carve_sortbufs(ctx, sb, n_max, chunk));
+    TTSK_TRY(carve_sortbufs(ctx, sb, n_max, chunk, d));
     if (!d_stage[0] || !d_stage[1] || !sk) {
         set_error("workspace carve failed");
         return TTSK_E_NOMEM;
@@ -1161,10 +1212,10 @@ static int operator_pass(ttsk_ctx* ctx, int64_t nnz, const int64_t* d_idx_mu, in
                          int64_t r_ps, int64_t r_cs, double* d_out, cudaStream_t st) {
     if (nnz == 0) return TTSK_OK;
     const int64_t n_b = d_idx_mu ? n_mu : 1;
-    TTSK_TRY(ctx->ws_reserve(sortbufs_bytes(n_b, nnz) + 4096));
+    TTSK_TRY(ctx->ws_reserve(sortbufs_bytes(n_b, nnz, 0) + 4096));
     ctx->ws_reset();
     SortBufs sb;
-    TTSK_TRY(carve_sortbufs(ctx, sb, n_b, nnz));
+    TTSK_TRY(carve_sortbufs(ctx, sb, n_b, nnz, 0));
     PassParams P;
     std::memset(&P, 0, sizeof(P));
     P.nnz = nnz;
