@@ -457,6 +457,10 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
                 }
                 const long long npos = s + kPiece + i;
                 w_next[u] = (P.keyid && npos < item_hi) ? P.keyid[npos] : 0ull;
+                // pull the NEXT piece's record into L2 now (its id is already in a register): the
+                // random 32-byte DRAM access then overlaps this piece's compute
+                if (P.recs && npos < item_hi && !(P.debug & 32))
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.recs + (w_next[u] & 0xffffffffull) * P.rec_words));
                 s_key[i] = key;
                 const unsigned* rec = P.recs ? P.recs + id * P.rec_words : nullptr;
                 s_val[i] = in ? (rec ? *reinterpret_cast<const double*>(rec) : P.val[id]) : 0.0;
