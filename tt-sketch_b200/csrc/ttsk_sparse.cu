@@ -77,7 +77,7 @@ struct PassParams {
     double* omega;   // (rA, rX), only with X
     // shared-memory plan (host computed)
     int pitchA, pitchB, pitchX;  // row pitch of each tile in doubles
-    int bufsA, bufsB, bufsX;     // 1, or 2 for gathered (cp.async double-buffered) sources
+    int bufsA, bufsB, bufsX;     // 1: tile in shared memory (generated / absent source), 0: gathered from global
     unsigned long long magicA, magicB, magicX;  // ceil(2^32 / r): thread id -> (row, column)
     int rpiA, rpiB, rpiX;        // rows covered per sweep of the 256 threads (256 / r)
     int queue_cap_w;             // tail-queue slots per warp
@@ -250,18 +250,6 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
 constexpr int kPassThreads = 256;
 constexpr int kPassWarps = kPassThreads / 32;
 constexpr int kPiece = 512;  // sorted positions staged per CTA iteration
@@ -270,27 +258,36 @@ constexpr int kPiece = 512;  // sorted positions staged per CTA iteration
 // MMA fragment loads (4 rows x 8 columns per warp) are bank-conflict free
 __host__ __device__ constexpr int tile_pitch(int tiles8) { return 8 * tiles8 + ((tiles8 % 2 == 0) ? 8 : 0); }
 
-// gather TN rows of a ROWS/TABLE source into a [TN][pitch] tile with cp.async
+// Gathered (ROWS / TABLE) sources are never staged in shared memory: every element is used by
+// exactly one lane of one MMA, so the fragments are loaded straight from global memory in the
+// accumulate stage.  To keep those loads out of DRAM latency the rows of the NEXT tile are pulled
+// into L2 one tile ahead.
 template <int TN>
-__device__ __forceinline__ void gather_rows_async(const Source& S, double* __restrict__ tile, int pitch,
-                                                  const unsigned long long* __restrict__ s_flat, int n_rows) {
-    const int tid = threadIdx.x;
-    const bool vec = (S.col_stride == 1) && ((S.r & 1) == 0) && ((S.row_stride & 1) == 0) &&
-                     ((reinterpret_cast<unsigned long long>(S.base) & 15ull) == 0);
-    if (vec) {
-        const int per_row = S.r >> 1;
-        const int total = n_rows * per_row;
-        for (int e = tid; e < total; e += kPassThreads) {
-            const int p = e / per_row, c = e - p * per_row;
-            cp_async16(tile + p * pitch + 2 * c, S.base + (long long)s_flat[p] * S.row_stride + 2 * c);
-        }
-    } else {
-        const int total = n_rows * S.r;
-        for (int e = tid; e < total; e += kPassThreads) {
-            const int p = e / S.r, a = e - p * S.r;
-            cp_async8(tile + p * pitch + a, S.base + (long long)s_flat[p] * S.row_stride + (long long)a * S.col_stride);
-        }
+__device__ __forceinline__ void prefetch_rows_l2(const Source& S, const unsigned long long* __restrict__ s_flat,
+                                                 int n_rows) {
+    if (S.col_stride != 1) return;  // column-strided rows (operator-level (r, nnz) layout): no contiguous row
+    const int lines = (S.r * 8 + 127) >> 7;
+    const int total = n_rows * lines;
+    for (int e = threadIdx.x; e < total; e += kPassThreads) {
+        const int p = e / lines, l = e - p * lines;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.base + (long long)s_flat[p] * S.row_stride + 16 * l));
     }
+}
+
+constexpr int kQueueCap = 256;  // tail-queue slots per warp (drained when nearly full)
+
+// the warp's deferred ndtri tails: dense over the queue, no divergence between lanes
+__device__ __forceinline__ void drain_tail_queue(double* At_c, double* Bt_c, double* Xt_c, const int* __restrict__ wq,
+                                                 int& wcount, const double2* __restrict__ s_tab) {
+    __syncwarp();
+    for (int qi = threadIdx.x & 31; qi < wcount; qi += 32) {
+        const int enc = wq[qi];
+        const int src = enc >> 28, cls = (enc >> 26) & 3, off = enc & 0x3ffffff;
+        double* tile = src == 0 ? At_c : (src == 1 ? Bt_c : Xt_c);
+        tile[off] = ndtri_tail(tile[off], cls, s_tab);
+    }
+    __syncwarp();
+    wcount = 0;
 }
 
 // hash-seeded Gaussian source -> [TN][pitch] tile.
@@ -305,7 +302,8 @@ __device__ __forceinline__ void fill_gauss(const Source& S, int rpi, unsigned lo
                                            double* __restrict__ tile, int pitch, int len,
                                            const unsigned long long* __restrict__ s_flat,
                                            const unsigned long long* __restrict__ s_salt, int* __restrict__ wq,
-                                           int& wcount, int debug) {
+                                           int& wcount, int debug, double* At_c, double* Bt_c, double* Xt_c,
+                                           const double2* __restrict__ s_tab) {
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int prow = (int)(((unsigned long long)(unsigned)tid * magic) >> 32);
@@ -331,6 +329,7 @@ __device__ __forceinline__ void fill_gauss(const Source& S, int rpi, unsigned lo
         const unsigned m1 = __ballot_sync(0xffffffffu, t1);
         if (t1) wq[wcount + __popc(m1 & lt)] = (src_id << 28) | (k1 << 26) | off1;
         wcount += __popc(m1);
+        if (wcount > kQueueCap - 64) drain_tail_queue(At_c, Bt_c, Xt_c, wq, wcount, s_tab);  // warp-uniform
     }
 }
 
@@ -368,9 +367,9 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const bool gatherA = !(P.debug & 4) && (P.A.kind == SRC_ROWS || P.A.kind == SRC_TABLE);
-    const bool gatherB = !(P.debug & 4) && (P.B.kind == SRC_ROWS || P.B.kind == SRC_TABLE);
-    const bool gatherX = !(P.debug & 4) && HAS_X && (P.X.kind == SRC_ROWS || P.X.kind == SRC_TABLE);
+    const bool gatherA = (P.A.kind == SRC_ROWS || P.A.kind == SRC_TABLE);
+    const bool gatherB = (P.B.kind == SRC_ROWS || P.B.kind == SRC_TABLE);
+    const bool gatherX = HAS_X && (P.X.kind == SRC_ROWS || P.X.kind == SRC_TABLE);
     int* wq = s_queue + warp * P.queue_cap_w;
 
     load_logtab(s_tab);
@@ -469,13 +468,12 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
                 if (HAS_X) s_fx[i] = in ? fold_flat(P.X, rec, id) : 0ull;
             }
             __syncthreads();
-            int c = 0, buf = 0;
-            {   // gather of the first tile
+            int c = 0;
+            if (!(P.debug & 4)) {  // rows of the piece's first tile -> L2
                 const int rows = (n_piece < TN) ? n_piece : TN;
-                if (gatherA) gather_rows_async<TN>(P.A, At, PA, s_fa, rows);
-                if (gatherB) gather_rows_async<TN>(P.B, Bt, PB, s_fb, rows);
-                if (gatherX) gather_rows_async<TN>(P.X, Xt, PX, s_fx, rows);
-                cp_async_commit();
+                if (gatherA) prefetch_rows_l2<TN>(P.A, s_fa, rows);
+                if (gatherB) prefetch_rows_l2<TN>(P.B, s_fb, rows);
+                if (gatherX) prefetch_rows_l2<TN>(P.X, s_fx, rows);
             }
             while (c < n_piece) {
                 // ---- run of equal keys starting at c, at most TN long (every warp computes it)
@@ -495,53 +493,69 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
                     }
                 }
                 const int next_c = c + len;
-                // ---- prefetch the gathered rows of the NEXT tile, then wait for this tile's
-                if (next_c < n_piece) {
+                // ---- rows of the NEXT tile -> L2 while this tile is generated and accumulated
+                if (next_c < n_piece && !(P.debug & 4)) {
                     const int rows = (n_piece - next_c < TN) ? n_piece - next_c : TN;
-                    const int nb = buf ^ 1;
-                    if (gatherA) gather_rows_async<TN>(P.A, At + nb * TR * PA, PA, s_fa + next_c, rows);
-                    if (gatherB) gather_rows_async<TN>(P.B, Bt + nb * TR * PB, PB, s_fb + next_c, rows);
-                    if (gatherX) gather_rows_async<TN>(P.X, Xt + nb * TR * PX, PX, s_fx + next_c, rows);
+                    if (gatherA) prefetch_rows_l2<TN>(P.A, s_fa + next_c, rows);
+                    if (gatherB) prefetch_rows_l2<TN>(P.B, s_fb + next_c, rows);
+                    if (gatherX) prefetch_rows_l2<TN>(P.X, s_fx + next_c, rows);
                 }
-                cp_async_commit();
-                cp_async_wait<1>();
                 if ((long long)key0 != cur_key) {
                     if (cur_key >= 0) flush_psi(cur_key);
                     cur_key = key0;
                 }
-                double* At_c = At + (P.bufsA == 2 ? buf * TR * PA : 0);
-                double* Bt_c = Bt + (P.bufsB == 2 ? buf * TR * PB : 0);
-                double* Xt_c = Xt + (HAS_X && P.bufsX == 2 ? buf * TR * PX : 0);
+                double* At_c = At;
+                double* Bt_c = Bt;
+                double* Xt_c = Xt;
                 // ---- on-the-fly sources, then this warp's deferred tails
                 int wcount = 0;
                 if (P.A.kind == SRC_GAUSS)
-                    fill_gauss<TN>(P.A, P.rpiA, P.magicA, 0, At_c, PA, len, s_fa + c, s_salt, wq, wcount, P.debug);
-                else if (P.A.kind == SRC_NONE && tid < TN) At_c[tid * PA] = 1.0;
+                    fill_gauss<TN>(P.A, P.rpiA, P.magicA, 0, At_c, PA, len, s_fa + c, s_salt, wq, wcount, P.debug, At_c, Bt_c, Xt_c, s_tab);
                 if (P.B.kind == SRC_GAUSS)
-                    fill_gauss<TN>(P.B, P.rpiB, P.magicB, 1, Bt_c, PB, len, s_fb + c, s_salt + 64, wq, wcount, P.debug);
-                else if (P.B.kind == SRC_NONE && tid < TN) Bt_c[tid * PB] = 1.0;
+                    fill_gauss<TN>(P.B, P.rpiB, P.magicB, 1, Bt_c, PB, len, s_fb + c, s_salt + 64, wq, wcount, P.debug, At_c, Bt_c, Xt_c, s_tab);
                 if (HAS_X && P.X.kind == SRC_GAUSS)
-                    fill_gauss<TN>(P.X, P.rpiX, P.magicX, 2, Xt_c, PX, len, s_fx + c, s_salt + 128, wq, wcount, P.debug);
-                __syncwarp();
-                for (int qi = lane; qi < wcount; qi += 32) {
-                    const int enc = wq[qi];
-                    const int src = enc >> 28, cls = (enc >> 26) & 3, off = enc & 0x3ffffff;
-                    double* tile = src == 0 ? At_c : (src == 1 ? Bt_c : Xt_c);
-                    tile[off] = ndtri_tail(tile[off], cls, s_tab);
-                }
+                    fill_gauss<TN>(P.X, P.rpiX, P.magicX, 2, Xt_c, PX, len, s_fx + c, s_salt + 128, wq, wcount, P.debug, At_c, Bt_c, Xt_c, s_tab);
+                drain_tail_queue(At_c, Bt_c, Xt_c, wq, wcount, s_tab);
                 __syncthreads();
-                // ---- accumulate: k-chunks of 4 nonzeros; A fragment scaled by the value
-                {
+                // ---- accumulate: k-chunks of 4 nonzeros; A fragment scaled by the value.  Fragments of
+                // generated sources come from the shared-memory tile, those of gathered sources
+                // straight from global memory (L2-resident thanks to the prefetch above).
+                if (!(P.debug & 2)) {
+                    const bool r_gather = omega_role ? gatherX : gatherB;
+                    const Source& RS = omega_role ? P.X : P.B;
                     const double* Rt = omega_role ? Xt_c : Bt_c;
                     const int PR = omega_role ? PX : PB;
-                    for (int ch = role_rank; ch * 4 < len && !(P.debug & 2); ch += role_warps) {
+                    const unsigned long long* s_fr = omega_role ? s_fx : s_fb;
+                    const int rR_cols = omega_role ? P.rX : P.rB;
+                    for (int ch = role_rank; ch * 4 < len; ch += role_warps) {
                         const int p0 = ch * 4 + q;
                         const double v = (p0 < len) ? s_val[c + p0] : 0.0;
+                        const int pr = (p0 < len) ? c + p0 : c;  // rows past the run read a valid row (scaled by v = 0)
                         double a[MI], b[NJ];
+                        if (gatherA) {
+                            const double* row = P.A.base + (long long)s_fa[pr] * P.A.row_stride;
 #pragma unroll
-                        for (int i = 0; i < MI; i++) a[i] = At_c[p0 * PA + 8 * i + g] * v;
+                            for (int i = 0; i < MI; i++)
+                                a[i] = (8 * i + g < P.rA && !(P.debug & 4)) ? __ldg(row + (long long)(8 * i + g) * P.A.col_stride) * v : 0.0;
+                        } else if (P.A.kind == SRC_NONE) {  // Psi_0: the left factor is the scalar 1
 #pragma unroll
-                        for (int j = 0; j < NJ; j++) b[j] = Rt[p0 * PR + 8 * j + g];
+                            for (int i = 0; i < MI; i++) a[i] = (i == 0 && g == 0) ? v : 0.0;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < MI; i++) a[i] = At_c[p0 * PA + 8 * i + g] * v;
+                        }
+                        if (r_gather) {
+                            const double* row = RS.base + (long long)s_fr[pr] * RS.row_stride;
+#pragma unroll
+                            for (int j = 0; j < NJ; j++)
+                                b[j] = (8 * j + g < rR_cols && !(P.debug & 4)) ? __ldg(row + (long long)(8 * j + g) * RS.col_stride) : 0.0;
+                        } else if (RS.kind == SRC_NONE) {  // Psi_{d-1}: the right factor is the scalar 1
+#pragma unroll
+                            for (int j = 0; j < NJ; j++) b[j] = (j == 0 && g == 0) ? 1.0 : 0.0;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < NJ; j++) b[j] = Rt[p0 * PR + 8 * j + g];
+                        }
 #pragma unroll
                         for (int i = 0; i < MI; i++)
 #pragma unroll
@@ -550,9 +564,7 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
                 }
                 __syncthreads();
                 c = next_c;
-                buf ^= 1;
             }
-            cp_async_wait<0>();
         }
         if (cur_key >= 0) flush_psi(cur_key);
     }
@@ -566,9 +578,9 @@ static int launch_pass_t(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     P.pitchA = tile_pitch(MI);
     P.pitchB = tile_pitch(NJ);
     P.pitchX = tile_pitch(NJ);
-    P.bufsA = gathered(P.A) ? 2 : 1;
-    P.bufsB = gathered(P.B) ? 2 : 1;
-    P.bufsX = HAS_X ? (gathered(P.X) ? 2 : 1) : 0;
+    P.bufsA = P.A.kind == SRC_GAUSS ? 1 : 0;
+    P.bufsB = P.B.kind == SRC_GAUSS ? 1 : 0;
+    P.bufsX = (HAS_X && P.X.kind == SRC_GAUSS) ? 1 : 0;
     auto magic = [](int r) { return (((unsigned long long)1 << 32) + (unsigned)r - 1) / (unsigned)r; };
     P.magicA = magic(P.A.r > 0 ? P.A.r : 1);
     P.magicB = magic(P.B.r > 0 ? P.B.r : 1);
@@ -576,11 +588,7 @@ static int launch_pass_t(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     P.rpiA = kPassThreads / (P.A.r > 0 ? P.A.r : 1);
     P.rpiB = kPassThreads / (P.B.r > 0 ? P.B.r : 1);
     P.rpiX = kPassThreads / (P.X.r > 0 ? P.X.r : 1);
-    int per_lane = 0;  // worst-case queued tails per lane and tile
-    if (P.A.kind == SRC_GAUSS) per_lane += (TN + P.rpiA - 1) / P.rpiA + 1;
-    if (P.B.kind == SRC_GAUSS) per_lane += (TN + P.rpiB - 1) / P.rpiB + 1;
-    if (HAS_X && P.X.kind == SRC_GAUSS) per_lane += (TN + P.rpiX - 1) / P.rpiX + 1;
-    P.queue_cap_w = 32 * per_lane + 32;
+    P.queue_cap_w = kQueueCap;
     const size_t tile_doubles = (size_t)P.bufsA * (TN + 1) * P.pitchA + (size_t)P.bufsB * (TN + 1) * P.pitchB +
                                 (size_t)P.bufsX * (TN + 1) * P.pitchX;
     const size_t smem = 128 * 16 + (size_t)kPiece * 8 * 4 + 192 * 8 + tile_doubles * 8 + (size_t)kPiece * 4 +
@@ -617,8 +625,8 @@ static int launch_pass_x(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     const int nj = (std::max(P.rB, HAS_X ? P.rX : 1) + 7) / 8;
     TTSK_ARG(mi <= 8 && nj <= 8, "sparse pass: DRM rank above 64 is not supported by the fused kernel");
 #define TTSK_PASS(MI_, NJ_)                                                            \
-    return (tn == 32) ? launch_pass_t<MI_, NJ_, HAS_X, 32>(ctx, P, st) : launch_pass_t<MI_, NJ_, HAS_X, 64>(ctx, P, st)
-    static const int tn = getenv("TTSK_TN") ? atoi(getenv("TTSK_TN")) : 64;
+    return (tn == 64) ? launch_pass_t<MI_, NJ_, HAS_X, 64>(ctx, P, st) : launch_pass_t<MI_, NJ_, HAS_X, 128>(ctx, P, st)
+    static const int tn = getenv("TTSK_TN") ? atoi(getenv("TTSK_TN")) : 128;
     const int MIr = mi <= 1 ? 1 : (mi <= 3 ? 3 : (mi <= 5 ? 5 : 8));
     const int NJr = nj <= 1 ? 1 : (nj <= 3 ? 3 : (nj <= 5 ? 5 : 8));
     switch (MIr * 10 + NJr) {
