@@ -571,6 +571,140 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
     if (omega_role) flush(P.omega, P.rX, P.rX);
 }
 
+// ------------------------------------------------------------------ TT-DRM chain step, bucketed
+// v_out[id, :] = v_in[id, :] @ core[:, i_m(id), :] for every nonzero, walked in the order sorted by
+// i_m: all nonzeros of a segment share the r_in x r_out core slice, which is staged once in shared
+// memory, and a tile of 64 nonzeros is a (64 x r_in) @ (r_in x r_out) product on DMMA.  (The
+// reference gathers an (r_in, nnz, r_out) array and einsums it: tensor_train_drm.py:60-69.)
+struct ChainParams {
+    long long nnz, n_mu;
+    const unsigned long long* keyid;
+    const int* offs;
+    long long work_items, item_len;
+    const double* core;   // (r_in, n_mu, r_out)
+    const double* v_in;   // (chunk, r_in) by nonzero id
+    double* v_out;        // (chunk, r_out) by nonzero id
+    int r_in, r_out, pitch;
+};
+
+template <int NJ>
+__global__ void __launch_bounds__(256) ttdrm_chain_kernel(const ChainParams C) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Gs = reinterpret_cast<double*>(smem_raw);                    // [r_in_pad][pitch]
+    const int r_in_pad = (C.r_in + 3) & ~3;
+    unsigned long long* s_w = reinterpret_cast<unsigned long long*>(Gs + r_in_pad * C.pitch);  // [64]
+    long long* s_bounds = reinterpret_cast<long long*>(s_w + 64);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int ksteps = r_in_pad >> 2;
+    for (long long item = blockIdx.x; item < C.work_items; item += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) {
+            long long lo = item * C.item_len, hi = (item + 1) * C.item_len;
+            if (hi > C.nnz || item == C.work_items - 1) hi = C.nnz;
+            if (item > 0) lo = snap_to_segment(C.offs, C.n_mu, lo, C.item_len / 2);
+            if (hi < C.nnz) hi = snap_to_segment(C.offs, C.n_mu, hi, C.item_len / 2);
+            s_bounds[0] = lo;
+            s_bounds[1] = hi;
+        }
+        __syncthreads();
+        const long long item_lo = s_bounds[0], item_hi = s_bounds[1];
+        long long cur_key = -1;
+        long long c = item_lo;
+        while (c < item_hi) {
+            __syncthreads();  // previous tile done with s_w / Gs
+            if (tid < 64) s_w[tid] = (c + tid < item_hi) ? C.keyid[c + tid] : ~0ull;
+            __syncthreads();
+            const int key0 = (int)(s_w[0] >> 32);
+            int len = 0;
+            {
+                bool open = true;
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    const unsigned long long w = s_w[t * 32 + lane];
+                    const bool same = (w != ~0ull) && ((int)(w >> 32) == key0);
+                    const unsigned m = __ballot_sync(0xffffffffu, same);
+                    if (open) {
+                        if (m == 0xffffffffu) len += 32;
+                        else { len += __ffs(~m) - 1; open = false; }
+                    }
+                }
+            }
+            if ((long long)key0 != cur_key) {  // stage this segment's core slice
+                cur_key = key0;
+                for (int e = tid; e < r_in_pad * C.pitch; e += 256) {
+                    const int a = e / C.pitch, b = e - a * C.pitch;
+                    Gs[e] = (a < C.r_in && b < C.r_out) ? C.core[((long long)a * C.n_mu + key0) * C.r_out + b] : 0.0;
+                }
+                __syncthreads();
+            }
+            const int row = 8 * warp + g;
+            if (8 * warp < len) {
+                const bool valid = row < len;
+                const long long id = valid ? (long long)(s_w[row] & 0xffffffffull) : 0;
+                const double* vin = C.v_in + id * C.r_in;
+                double acc[NJ][2];
+#pragma unroll
+                for (int j = 0; j < NJ; j++) acc[j][0] = acc[j][1] = 0.0;
+                for (int kk = 0; kk < ksteps; kk++) {
+                    const int k = 4 * kk + q;
+                    const double a = (valid && k < C.r_in) ? __ldg(vin + k) : 0.0;
+#pragma unroll
+                    for (int j = 0; j < NJ; j++) dmma(acc[j][0], acc[j][1], a, Gs[k * C.pitch + 8 * j + g]);
+                }
+                if (valid) {
+                    double* vout = C.v_out + id * C.r_out;
+#pragma unroll
+                    for (int j = 0; j < NJ; j++) {
+                        const int col = 8 * j + 2 * q;
+                        if (col < C.r_out) vout[col] = acc[j][0];
+                        if (col + 1 < C.r_out) vout[col + 1] = acc[j][1];
+                    }
+                }
+            }
+            c += len;
+        }
+    }
+}
+
+template <int NJ>
+static int launch_chain_t(ttsk_ctx* ctx, ChainParams& C, cudaStream_t st) {
+    auto kern = ttdrm_chain_kernel<NJ>;
+    C.pitch = tile_pitch(NJ);
+    const int r_in_pad = (C.r_in + 3) & ~3;
+    const size_t smem = (size_t)r_in_pad * C.pitch * 8 + 64 * 8 + 64;
+    TTSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    TTSK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    long long items = grid * 8;
+    const long long min_len = 2048;
+    if (items * min_len > C.nnz) items = (C.nnz + min_len - 1) / min_len;
+    if (items < 1) items = 1;
+    C.work_items = items;
+    C.item_len = (C.nnz + items - 1) / items;
+    if (grid > items) grid = items;
+    kern<<<(unsigned)grid, 256, smem, st>>>(C);
+    TTSK_LAUNCHED(ctx);
+    return TTSK_OK;
+}
+
+static int launch_chain(ttsk_ctx* ctx, ChainParams& C, cudaStream_t st) {
+    const int nj = (C.r_out + 7) / 8;
+    TTSK_ARG(nj <= 8 && C.r_in <= 64, "TT-DRM chain: core rank above 64 is not supported by the bucketed kernel");
+    switch (nj) {
+        case 1: return launch_chain_t<1>(ctx, C, st);
+        case 2: return launch_chain_t<2>(ctx, C, st);
+        case 3: return launch_chain_t<3>(ctx, C, st);
+        case 4: return launch_chain_t<4>(ctx, C, st);
+        case 5: return launch_chain_t<5>(ctx, C, st);
+        case 6: return launch_chain_t<6>(ctx, C, st);
+        case 7: return launch_chain_t<7>(ctx, C, st);
+        default: return launch_chain_t<8>(ctx, C, st);
+    }
+}
+
 template <int MI, int NJ, bool HAS_X, int TN>
 static int launch_pass_t(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     auto kern = sparse_pass_kernel<MI, NJ, HAS_X, TN>;
@@ -844,17 +978,30 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
                         const ttsk_drm* right, double* out, SortBufs& sb, cudaStream_t st) {
     if (nnz <= 0) return TTSK_OK;
     const SketchLayout& lay = pl.lay;
-    // TT-DRM chains for this chunk (tensor_train_drm.py:60-69)
-    if (left->kind == TTSK_DRM_TT)
-        for (int k = 0; k < d - 1; k++)
-            TTSK_TRY(ttdrm_step(ctx, nnz, (const long long*)(d_idx + k * idx_row_stride),
-                                k == 0 ? nullptr : pl.left.chain[k - 1], left->core_r0[k], left->d_cores[k],
-                                shape[k], left->core_r1[k], pl.left.chain[k], st));
-    if (right->kind == TTSK_DRM_TT)
-        for (int k = 0; k < d - 1; k++)
-            TTSK_TRY(ttdrm_step(ctx, nnz, (const long long*)(d_idx + (d - 1 - k) * idx_row_stride),
-                                k == 0 ? nullptr : pl.right.chain[k - 1], right->core_r0[k], right->d_cores[k],
-                                shape[d - 1 - k], right->core_r1[k], pl.right.chain[k], st));
+    // TT-DRM chains for this chunk (tensor_train_drm.py:60-69): level 0 is a row gather of the first
+    // core; every further level is one bucketed pass over the nonzeros sorted by that level's mode
+    for (int side = 0; side < 2; side++) {
+        const ttsk_drm* drm = side == 0 ? left : right;
+        SideState& ss = side == 0 ? pl.left : pl.right;
+        if (drm->kind != TTSK_DRM_TT) continue;
+        for (int k = 0; k < d - 1; k++) {
+            const int mode = side == 0 ? k : d - 1 - k;
+            const long long* idx_m = (const long long*)(d_idx + mode * idx_row_stride);
+            const bool bucketed = k > 0 && nnz >= 4096 && drm->core_r1[k] <= 64 && drm->core_r0[k] <= 64;
+            if (!bucketed) {
+                TTSK_TRY(ttdrm_step(ctx, nnz, idx_m, k == 0 ? nullptr : ss.chain[k - 1], drm->core_r0[k],
+                                    drm->d_cores[k], shape[mode], drm->core_r1[k], ss.chain[k], st));
+                continue;
+            }
+            TTSK_TRY(sort_keys(ctx, nnz, idx_m, shape[mode], sb, st));
+            ChainParams C;
+            std::memset(&C, 0, sizeof(C));
+            C.nnz = nnz; C.n_mu = shape[mode]; C.keyid = sb.keyid; C.offs = sb.offs;
+            C.core = drm->d_cores[k]; C.v_in = ss.chain[k - 1]; C.v_out = ss.chain[k];
+            C.r_in = drm->core_r0[k]; C.r_out = drm->core_r1[k];
+            TTSK_TRY(launch_chain(ctx, C, st));
+        }
+    }
     const long long* idx_rows[TTSK_MAX_ORDER];
     for (int m = 0; m < d; m++) idx_rows[m] = (const long long*)(d_idx + m * idx_row_stride);
     {

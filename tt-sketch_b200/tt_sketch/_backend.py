@@ -166,6 +166,19 @@ def to_host(t) -> np.ndarray:
     return t.detach().cpu().numpy()
 
 
+def to_host_pinned(t) -> np.ndarray:
+    """Device -> host through a pinned buffer from torch's caching host allocator (full PCIe rate
+    instead of the driver's pageable staging).  The returned array owns the pinned block through
+    its base tensor, so the block is only recycled once the caller drops the array."""
+    torch = _torch()
+    if t.numel() * t.element_size() < (1 << 20):
+        return to_host(t)
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
 def ptr(t):
     return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
 

@@ -106,7 +106,11 @@ def distributed_stream_sketch(tensor: Tensor, left_drm, right_drm, group=None,
         raise ValueError("local sketch has the wrong packed length")
     if world > 1:
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-    return SketchContainer.unpack(packed.detach().cpu().numpy(), shape, rL, rR)
+    if packed.is_cuda:
+        from tt_sketch import _backend as be
+
+        return SketchContainer.unpack(be.to_host_pinned(packed), shape, rL, rR, copy=False)
+    return SketchContainer.unpack(packed.detach().numpy(), shape, rL, rR)
 
 
 def distributed_blocked_stream_sketch(tensor: Tensor, left_drm, right_drm, left_rank_slices, right_rank_slices,

@@ -47,12 +47,16 @@ class SketchContainer:
         return cls(arrays[:d], arrays[d:], tuple(shape), tuple(left_rank), tuple(right_rank))
 
     @classmethod
-    def unpack(cls, flat: np.ndarray, shape, left_rank, right_rank) -> "SketchContainer":
+    def unpack(cls, flat: np.ndarray, shape, left_rank, right_rank, copy: bool = True) -> "SketchContainer":
+        """Split a packed buffer into Psi cores and Omega matrices.  With copy=False the arrays are
+        views of `flat` (which must then be a fresh buffer owned by nobody else)."""
         items, total = cls.layout(shape, left_rank, right_rank)
         if flat.size != total:
             raise ValueError("packed sketch has the wrong length")
         d = len(shape)
-        arrays = [flat[o:o + int(np.prod(s))].reshape(s).copy() for o, s in items]
+        arrays = [flat[o:o + int(np.prod(s))].reshape(s) for o, s in items]
+        if copy:
+            arrays = [a.copy() for a in arrays]
         return cls(arrays[:d], arrays[d:])
 
     def pack(self) -> np.ndarray:

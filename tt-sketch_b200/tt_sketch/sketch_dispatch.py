@@ -297,5 +297,5 @@ def general_sketch(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, meth
         raise ValueError(f"left_drm must be provided for method '{method}'")
     if method == SketchMethod.streaming:
         packed, (shape, rL, rR) = streaming_sketch_device(tensor, left_drm, right_drm)
-        return SketchContainer.unpack(be.to_host(packed), shape, rL, rR)
+        return SketchContainer.unpack(be.to_host_pinned(packed), shape, rL, rR, copy=False)
     return _sequential_sketch(tensor, left_drm, right_drm, method)
