@@ -106,6 +106,7 @@ int ttsk_destroy(ttsk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->ws) cudaFree(ctx->ws);
+    for (auto& t : ctx->tables) cudaFree(t.ptr);
     for (int i = 0; i < 2; i++) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);

@@ -70,6 +70,10 @@ struct ttsk_ctx {
     std::vector<cudaEvent_t> ev_pass;  // pairs (start, stop) around every pass kernel
     int n_pass_events = 0;
     bool timing = true;
+    // prefix tables of Gaussian DRMs depend only on (seed, column range, rows): kept across calls
+    struct TableEntry { uint64_t seed; int rank_min, r; int64_t rows; double* ptr; int64_t bytes; cudaStream_t stream; };
+    std::vector<TableEntry> tables;
+    int64_t table_bytes = 0;
 
     int ws_reserve(int64_t bytes);              // make the arena at least this large (may sync)
     void ws_reset() { ws_used = 0; }

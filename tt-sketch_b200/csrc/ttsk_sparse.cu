@@ -1053,6 +1053,40 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
     return TTSK_OK;
 }
 
+// Prefix tables are a function of the DRM alone (seed, column range, number of rows), so they are
+// generated once per context and reused by later sketches with the same DRM (streaming updates,
+// blocked sketches, repeated calls).  Cache capped at 6 GB, oldest entries dropped first.
+static int cached_gauss_table(ttsk_ctx* ctx, int64_t rows, int rank_min, int r, uint64_t seed, double** out,
+                              cudaStream_t st) {
+    for (auto& t : ctx->tables)
+        if (t.seed == seed && t.rank_min == rank_min && t.r == r && t.rows == rows) {
+            if (t.stream != st) TTSK_CUDA(cudaStreamSynchronize(t.stream));  // filled on another stream
+            t.stream = st;
+            *out = t.ptr;
+            return TTSK_OK;
+        }
+    const int64_t bytes = rows * (int64_t)r * 8;
+    const int64_t cap = (int64_t)6 << 30;
+    while (!ctx->tables.empty() && ctx->table_bytes + bytes > cap) {
+        TTSK_CUDA(cudaDeviceSynchronize());
+        TTSK_CUDA(cudaFree(ctx->tables.front().ptr));
+        ctx->table_bytes -= ctx->tables.front().bytes;
+        ctx->tables.erase(ctx->tables.begin());
+    }
+    double* p = nullptr;
+    cudaError_t e = cudaMalloc((void**)&p, (size_t)bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("DRM table allocation of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+        return TTSK_E_NOMEM;
+    }
+    TTSK_TRY(gauss_table_launch(ctx, rows, rank_min, r, seed, p, st));
+    ctx->tables.push_back({seed, rank_min, r, rows, p, bytes, st});
+    ctx->table_bytes += bytes;
+    *out = p;
+    return TTSK_OK;
+}
+
 // Build the per-bond sources (tables are generated here; chain buffers are carved per chunk)
 static int build_plan(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* shape, int64_t nnz_total,
                       int64_t chunk, const ttsk_drm* left, const ttsk_drm* right, cudaStream_t st) {
@@ -1079,9 +1113,8 @@ static int build_plan(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* shape
                 const bool edge = (side == 0 && bond == 0) || (side == 1 && bond == d - 2);
                 const bool small = rows > 0 && rows <= table_rows_cap && rows * S.r * 8 <= table_bytes_cap;
                 if (small || (edge && rows > 0)) {
-                    double* tab = (double*)ctx->ws_alloc(rows * (int64_t)S.r * 8);
-                    if (!tab) { set_error("workspace too small for DRM table"); return TTSK_E_NOMEM; }
-                    TTSK_TRY(gauss_table_launch(ctx, rows, S.rank_min, S.r, S.seed, tab, st));
+                    double* tab = nullptr;
+                    TTSK_TRY(cached_gauss_table(ctx, rows, S.rank_min, S.r, S.seed, &tab, st));
                     if (edge && side == 0) pl.edge_L0 = tab;
                     if (edge && side == 1) pl.edge_R = tab;
                     if (small) {
