@@ -1100,7 +1100,7 @@ static int build_plan(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* shape
     for (int mu = 0; mu < d; mu++) pl.n_max = std::max<int64_t>(pl.n_max, shape[mu]);
     pl.edge_L0 = nullptr;
     pl.edge_R = nullptr;
-    const int64_t table_rows_cap = std::max<int64_t>(nnz_total / 4, 1);
+    const int64_t table_rows_cap = std::max<int64_t>(nnz_total, 1);  // a table row is cheaper than two on-the-fly rows and is cached
     const int64_t table_bytes_cap = (int64_t)4 << 30;
     for (int side = 0; side < 2; side++) {
         const ttsk_drm* drm = side == 0 ? left : right;
@@ -1149,7 +1149,7 @@ static int64_t plan_workspace_bytes(int d, const int64_t* shape, int64_t nnz_tot
     auto add = [&](int64_t b) { bytes = align_up(bytes, 256) + b; };
     add(sketch_elems * 8);                  // temp sketch when accumulating
     add(sortbufs_bytes(n_max, chunk, d));   // hist/offs/cursor + sorted (key, id) words + packed records
-    const int64_t table_rows_cap = std::max<int64_t>(nnz_total / 4, 1);
+    const int64_t table_rows_cap = std::max<int64_t>(nnz_total, 1);  // a table row is cheaper than two on-the-fly rows and is cached
     for (int side = 0; side < 2; side++) {
         const ttsk_drm* drm = side == 0 ? left : right;
         for (int bond = 0; bond < d - 1; bond++) {
