@@ -64,6 +64,19 @@ def make_coo(nnz, lo, hi):
     return idx, val
 
 
+def measured_traffic(nnz):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the pass kernel, per launch, from the committed
+    ncu --set full capture of this workload (profiles/r01_pass_traffic_1e8nnz.json); None for other sizes."""
+    path = os.path.join(ROOT, "profiles", "r01_pass_traffic_1e8nnz.json")
+    try:
+        d = json.load(open(path))
+        if int(d["nnz"]) == int(nnz):
+            return float(d["dram_bytes_per_launch_avg"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -338,7 +351,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(nnz, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": which, "kernel": "ttsk::sparse_pass_kernel",
+                         "traffic": measured_traffic(nnz) if world == 1 else None, "peak_source": which,
+                         "kernel": "ttsk::sparse_pass_kernel", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_NNZ * n_loc / n_pass,
                          "launches_per_step": n_pass,
                          "note": "algorithmic 40 B/nnz over the d=4 mode passes (10 B/nnz per launch) / summed pass "
                                  "time of the last step; the kernel is FP64-issue-bound (bit-exact ndtri), see "
