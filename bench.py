@@ -292,6 +292,10 @@ def main():
     a, b = c_double(), c_double()
     be.check(lib.ttsk_last_kernel_ms(ctx, byref(a), byref(b)))
     step_kernels_ms, pass_kernels_ms = a.value, b.value
+    from ctypes import c_int
+    pm, pn = (c_double * 64)(), c_int()
+    be.check(lib.ttsk_last_pass_ms(ctx, pm, 64, byref(pn)))
+    per_pass_ms = [pm[i] for i in range(min(pn.value, 64))]
     t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
@@ -358,7 +362,8 @@ def main():
                                  "time of the last step; the kernel is FP64-issue-bound (bit-exact ndtri), see "
                                  "fp64_pipe and DESIGN.md section 5"},
             "fp64_pipe": fp64_model(n_loc, pass_kernels_ms),
-            "kernel_ms": {"pass_kernels_last_step": pass_kernels_ms, "all_kernels_last_step": step_kernels_ms},
+            "kernel_ms": {"pass_kernels_last_step": pass_kernels_ms, "all_kernels_last_step": step_kernels_ms,
+                          "per_pass_last_step": per_pass_ms},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "host": {"coo_generation_s": gen_s, "cpu_count": os.cpu_count()},
             "checksum": checksum,

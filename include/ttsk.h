@@ -60,6 +60,8 @@ int64_t ttsk_launch_count(ttsk_ctx *ctx);
 /* Milliseconds spent in the sketch kernels of the most recent ttsk_sparse_sketch* call,
  * measured with CUDA events on the launching stream (synchronises). */
 int ttsk_last_kernel_ms(ttsk_ctx *ctx, double *ms_total, double *ms_dominant);
+/* Per-launch milliseconds of the dominant (mode pass) kernel in that call: fills ms[0..min(cap, n)) and returns n in *n_out. */
+int ttsk_last_pass_ms(ttsk_ctx *ctx, double *ms, int cap, int *n_out);
 
 /* ---------------------------------------------------------------- lazy Gaussian DRM
  * Replaces inds_to_normal(indices, shape, rank_min, rank_max, seed)

@@ -11,7 +11,7 @@ using namespace ttsk;
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k(double* out, int iters, unsigned long long seed) {
-    __shared__ double2 s_tab[128];
+    __shared__ double2 s_tab[ttsk::kGaussTabEntries];
     load_logtab(s_tab);
     __syncthreads();
     unsigned long long f0 = seed + threadIdx.x + 977ull * blockIdx.x, f1 = f0 * 31 + 7;

@@ -17,7 +17,7 @@ constexpr int kMaxSalts = 2048;
 // the k index loads of a warp hit one or two addresses.
 __global__ void __launch_bounds__(256) lazy_gaussian_kernel(GaussIdx gi, long long nnz, int rank_min, int rank,
                                                            unsigned long long seed, double* __restrict__ out) {
-    __shared__ double2 s_tab[128];
+    __shared__ double2 s_tab[kGaussTabEntries];
     __shared__ unsigned long long s_salt[kMaxSalts];
     load_logtab(s_tab);
     for (int a = threadIdx.x; a < rank && a < kMaxSalts; a += blockDim.x)

@@ -46,6 +46,7 @@ struct Source {
     unsigned long long seed;
     const double* base;  // ROWS / TABLE: element (q, a) at base[q*row_stride + a*col_stride]
     long long row_stride, col_stride;
+    long long span_bytes;  // ROWS / TABLE: size of the gathered array (0: unknown); small arrays live in L2 and are not prefetched
 };
 
 // The bucket scatter writes ONE packed word per nonzero in sorted order: (key << 32) | id with
@@ -75,16 +76,19 @@ struct PassParams {
     int rA, rB, rX;  // logical tile widths (1 for SRC_NONE)
     double* psi;     // (rA, n_mu, rB)
     double* omega;   // (rA, rX), only with X
-    // shared-memory plan (host computed)
-    int pitchA, pitchB, pitchX;  // row pitch of each tile in doubles
-    int bufsA, bufsB, bufsX;     // 1: tile in shared memory (generated / absent source), 0: gathered from global
-    unsigned long long magicA, magicB, magicX;  // ceil(2^32 / r): thread id -> (row, column)
-    int rpiA, rpiB, rpiX;        // rows covered per sweep of the 256 threads (256 / r)
-    int queue_cap_w;             // tail-queue slots per warp
+    // shared-memory plan (host computed), per source s = 0 (A), 1 (B), 2 (X)
+    int pitch[3];    // row pitch of the tile in doubles
+    int bufs[3];     // tile stages: 0 absent source, 1 generated in place, 2 gathered (double-buffered cp.async)
+    int units[3];    // work units per row: columns (generated), 16-byte chunks or single doubles (gathered)
+    int vec[3];      // gathered: 1 = contiguous 16-byte-aligned rows (16-byte copies)
+    int toff[3];     // offset of the source's first stage in the tile area (doubles)
+    int pf[3];       // gathered: pull the rows of the next piece into L2 while the current piece is processed
+    int pf_any;
+    int queue_cap;   // 16-bit tail-queue slots per warp (worst case of one source's tile: no overflow possible)
     int smem_bytes;
     const int* offs;             // segment starts in the sorted order (n_mu + 1), or nullptr
     long long work_items, item_len;
-    int debug;  // ablation switches for profiling (TTSK_ABLATE): 1 no ndtri, 2 no MMA, 4 no gathers, 8 no flush, 16 no tails
+    int debug;  // profiling switches (TTSK_ABLATE), tested once per tile: 1 no generation, 2 no MMA, 4 no row gathers, 8 no L2 row prefetch
 };
 
 // ------------------------------------------------------------------ bucketing (counting sort)
@@ -252,86 +256,35 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 constexpr int kPassThreads = 256;
 constexpr int kPassWarps = kPassThreads / 32;
-constexpr int kPiece = 512;  // sorted positions staged per CTA iteration
-
+// sorted positions staged per CTA iteration, for a tile height tn
+__host__ __device__ constexpr int piece_for(int tn) { return tn <= 64 ? 256 : 512; }
 // row pitch (doubles) of a tile with `tiles8` 8-wide MMA column tiles: == 8 (mod 16) so the
 // MMA fragment loads (4 rows x 8 columns per warp) are bank-conflict free
 __host__ __device__ constexpr int tile_pitch(int tiles8) { return 8 * tiles8 + ((tiles8 % 2 == 0) ? 8 : 0); }
 
-// Gathered (ROWS / TABLE) sources are never staged in shared memory: every element is used by
-// exactly one lane of one MMA, so the fragments are loaded straight from global memory in the
-// accumulate stage.  To keep those loads out of DRAM latency the rows of the NEXT tile are pulled
-// into L2 one tile ahead.
-template <int TN>
-__device__ __forceinline__ void prefetch_rows_l2(const Source& S, const unsigned long long* __restrict__ s_flat,
-                                                 int n_rows) {
-    if (S.col_stride != 1) return;  // column-strided rows (operator-level (r, nnz) layout): no contiguous row
-    const int lines = (S.r * 8 + 127) >> 7;
-    const int total = n_rows * lines;
-    for (int e = threadIdx.x; e < total; e += kPassThreads) {
-        const int p = e / lines, l = e - p * lines;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.base + (long long)s_flat[p] * S.row_stride + 16 * l));
-    }
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Role of a thread inside one source's tile: it owns unit `col` (a column of a generated source,
+// a 16-byte or 8-byte chunk of a gathered row) and walks the rows prow, prow + rpi, ...
+// Threads that do not fit (256 % units) get prow = 1 << 20 so every row test fails for them.
+__host__ __device__ inline int rows_per_sweep(int units, int max_rows) {
+    int rpi = kPassThreads / units;
+    if (rpi > max_rows) rpi = max_rows;
+    return rpi < 1 ? 1 : rpi;
 }
 
-constexpr int kQueueCap = 256;  // tail-queue slots per warp (drained when nearly full)
-
-// the warp's deferred ndtri tails: dense over the queue, no divergence between lanes
-__device__ __forceinline__ void drain_tail_queue(double* At_c, double* Bt_c, double* Xt_c, const int* __restrict__ wq,
-                                                 int& wcount, const double2* __restrict__ s_tab) {
-    __syncwarp();
-    for (int qi = threadIdx.x & 31; qi < wcount; qi += 32) {
-        const int enc = wq[qi];
-        const int src = enc >> 28, cls = (enc >> 26) & 3, off = enc & 0x3ffffff;
-        double* tile = src == 0 ? At_c : (src == 1 ? Bt_c : Xt_c);
-        tile[off] = ndtri_tail(tile[off], cls, s_tab);
-    }
-    __syncwarp();
-    wcount = 0;
-}
-
-// hash-seeded Gaussian source -> [TN][pitch] tile.
-// Thread t owns ONE column a = t % r (its salt lives in a register) and walks the rows
-// p = t / r, + rpi, + 2 rpi ... (rpi = 256 / r rows per sweep; 256 % r threads idle).  Two rows
-// are processed per iteration so two independent hash / Horner chains are in flight.  The
-// central branch of ndtri is evaluated for every lane without a branch (a diverged warp would
-// issue it anyway); lanes whose uniform falls in a tail keep the uniform in the tile and push
-// the slot on the warp's private queue, which the same warp drains densely afterwards.
-template <int TN>
-__device__ __forceinline__ void fill_gauss(const Source& S, int rpi, unsigned long long magic, int src_id,
-                                           double* __restrict__ tile, int pitch, int len,
-                                           const unsigned long long* __restrict__ s_flat,
-                                           const unsigned long long* __restrict__ s_salt, int* __restrict__ wq,
-                                           int& wcount, int debug, double* At_c, double* Bt_c, double* Xt_c,
-                                           const double2* __restrict__ s_tab) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const int prow = (int)(((unsigned long long)(unsigned)tid * magic) >> 32);
-    const int a = tid - prow * S.r;
-    const bool active = prow < rpi;
-    const unsigned long long salt = active ? s_salt[a] : 0ull;
-    const int sweeps = (len + rpi - 1) / rpi;
-    for (int it = 0; it < sweeps; it += 2) {
-        const int p0 = prow + it * rpi, p1 = p0 + rpi;
-        const bool v0 = active && p0 < len, v1 = active && p1 < len;
-        const double u0 = uniform_from_hash(hash64((v0 ? s_flat[p0] : 0ull) + salt));
-        const double u1 = uniform_from_hash(hash64((v1 ? s_flat[p1] : 0ull) + salt));
-        const double c0 = (debug & 1) ? u0 : ndtri_central(u0), c1 = (debug & 1) ? u1 : ndtri_central(u1);
-        const int k0 = (debug & 17) ? 0 : ndtri_class(u0), k1 = (debug & 17) ? 0 : ndtri_class(u1);
-        const bool t0 = v0 && k0 != 0, t1 = v1 && k1 != 0;
-        // rows that do not exist write to the spare row TN so both chains stay branch-free
-        const int off0 = (v0 ? p0 : TN) * pitch + (active ? a : 0), off1 = (v1 ? p1 : TN) * pitch + (active ? a : 0);
-        tile[off0] = t0 ? u0 : c0;
-        tile[off1] = t1 ? u1 : c1;
-        const unsigned m0 = __ballot_sync(0xffffffffu, t0);
-        if (t0) wq[wcount + __popc(m0 & lt)] = (src_id << 28) | (k0 << 26) | off0;
-        wcount += __popc(m0);
-        const unsigned m1 = __ballot_sync(0xffffffffu, t1);
-        if (t1) wq[wcount + __popc(m1 & lt)] = (src_id << 28) | (k1 << 26) | off1;
-        wcount += __popc(m1);
-        if (wcount > kQueueCap - 64) drain_tail_queue(At_c, Bt_c, Xt_c, wq, wcount, s_tab);  // warp-uniform
-    }
-}
+// high 20 mantissa bits of a uniform that may lie in a tail of ndtri: u <= exp(-2) needs
+// hi <= 141909, u > 1 - exp(-2) needs hi >= 906666 (conservative by one word each side)
+constexpr unsigned kCentralLo = 141910u, kCentralSpan = 906666u - 141910u;
 
 // first sorted position >= x that starts a segment, if it is within `slack` of x; else x
 __device__ __forceinline__ long long snap_to_segment(const int* __restrict__ offs, long long n_mu, long long x,
@@ -345,52 +298,54 @@ __device__ __forceinline__ long long snap_to_segment(const int* __restrict__ off
     return (b - x <= slack) ? b : x;
 }
 
-// MI/NJ: 8x8 MMA tiles covering rA / max(rB, rX).  HAS_X: warps 4..7 accumulate
-// Omega = (v At)^T Xt while warps 0..3 accumulate Psi = (v At)^T Bt.
+// MI/NJ: 8x8 MMA tiles covering rA / max(rB, rX).  TN: rows of a tile.  The sorted order of a
+// work item is cut into pieces of kPiece positions and every piece into tiles of TN positions on
+// a fixed grid (independent of segment boundaries).  Per tile: asynchronous gathers of the NEXT
+// tile's table rows are issued, the generated sources of THIS tile are produced, then every warp
+// accumulates its own TN/8 rows (TN/4 with HAS_X: warps 0..3 Psi = (v At)^T Bt, warps 4..7
+// Omega = (v At)^T Xt) with FP64 MMAs, flushing its Psi accumulators whenever the key changes.
 template <int MI, int NJ, bool HAS_X, int TN>
-__global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassParams P) {
+__global__ void __launch_bounds__(kPassThreads, (MI * NJ <= 5) ? 3 : ((MI * NJ <= 15) ? 2 : 1)) sparse_pass_kernel(const PassParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int PA = P.pitchA, PB = P.pitchB, PX = P.pitchX;
-    double2* s_tab = reinterpret_cast<double2*>(smem_raw);  // 128 x 16 B
-    double* s_val = reinterpret_cast<double*>(s_tab + 128);  // [kPiece]
-    unsigned long long* s_fa = reinterpret_cast<unsigned long long*>(s_val + kPiece);
-    unsigned long long* s_fb = s_fa + kPiece;
-    unsigned long long* s_fx = s_fb + kPiece;
-    unsigned long long* s_salt = s_fx + kPiece;              // [3][64]
-    double* At = reinterpret_cast<double*>(s_salt + 192);    // [bufsA][TN][PA]
-    constexpr int TR = TN + 1;  // one spare row per tile
-    double* Bt = At + P.bufsA * TR * PA;
-    double* Xt = Bt + P.bufsB * TR * PB;
-    int* s_key = reinterpret_cast<int*>(Xt + (HAS_X ? P.bufsX * TR * PX : 0));  // [kPiece]
-    int* s_queue = s_key + kPiece;                           // [kPassWarps][queue_cap_w]
-    long long* s_bounds = reinterpret_cast<long long*>(s_queue + kPassWarps * P.queue_cap_w + (P.queue_cap_w & 1));
+    constexpr int kPiece = piece_for(TN);
+    double2* s_tab = reinterpret_cast<double2*>(smem_raw);  // log table + tail coefficients
+    double* s_val = reinterpret_cast<double*>(s_tab + kGaussTabEntries);  // [kPiece]
+    unsigned long long* s_flat = reinterpret_cast<unsigned long long*>(s_val + kPiece);  // [3][kPiece]
+    unsigned long long* s_salt = s_flat + 3 * kPiece;        // [3][64]
+    int* s_key = reinterpret_cast<int*>(s_salt + 192);       // [kPiece]
+    long long* s_bounds = reinterpret_cast<long long*>(s_key + kPiece);  // [2]
+    double* tiles = reinterpret_cast<double*>(s_bounds + 2);
+    constexpr int NS = HAS_X ? 3 : 2;
+    int tile_doubles = 0;
+#pragma unroll
+    for (int k = 0; k < NS; k++) tile_doubles += P.bufs[k] * TN * P.pitch[k];
+    unsigned short* s_queue = reinterpret_cast<unsigned short*>(tiles + tile_doubles);  // [kPassWarps][queue_cap]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const bool gatherA = (P.A.kind == SRC_ROWS || P.A.kind == SRC_TABLE);
-    const bool gatherB = (P.B.kind == SRC_ROWS || P.B.kind == SRC_TABLE);
-    const bool gatherX = HAS_X && (P.X.kind == SRC_ROWS || P.X.kind == SRC_TABLE);
-    int* wq = s_queue + warp * P.queue_cap_w;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned short* wq = s_queue + warp * P.queue_cap;
+    bool any_gather = false;
+#pragma unroll
+    for (int k = 0; k < NS; k++) any_gather |= P.bufs[k] == 2;
 
     load_logtab(s_tab);
-    {
-        const int tile_doubles = P.bufsA * TR * PA + P.bufsB * TR * PB + (HAS_X ? P.bufsX * TR * PX : 0);
-        for (int i = tid; i < tile_doubles; i += kPassThreads) At[i] = 0.0;
+    for (int i = tid; i < tile_doubles; i += kPassThreads) tiles[i] = 0.0;
+    if (tid < 64) {
+        if (P.A.kind == SRC_GAUSS && tid < P.A.r) s_salt[tid] = hash64((unsigned long long)(P.A.rank_min + tid)) + P.A.seed;
+        if (P.B.kind == SRC_GAUSS && tid < P.B.r) s_salt[64 + tid] = hash64((unsigned long long)(P.B.rank_min + tid)) + P.B.seed;
+        if (HAS_X && P.X.kind == SRC_GAUSS && tid < P.X.r) s_salt[128 + tid] = hash64((unsigned long long)(P.X.rank_min + tid)) + P.X.seed;
     }
-    if (P.A.kind == SRC_GAUSS)
-        for (int a = tid; a < P.A.r; a += kPassThreads)
-            s_salt[a] = hash64((unsigned long long)(P.A.rank_min + a)) + P.A.seed;
-    if (P.B.kind == SRC_GAUSS)
-        for (int a = tid; a < P.B.r; a += kPassThreads)
-            s_salt[64 + a] = hash64((unsigned long long)(P.B.rank_min + a)) + P.B.seed;
-    if (HAS_X && P.X.kind == SRC_GAUSS)
-        for (int a = tid; a < P.X.r; a += kPassThreads)
-            s_salt[128 + a] = hash64((unsigned long long)(P.X.rank_min + a)) + P.X.seed;
 
     // role of this warp in the accumulate stage
     const bool omega_role = HAS_X && warp >= kPassWarps / 2;
-    const int role_warps = HAS_X ? kPassWarps / 2 : kPassWarps;
-    const int role_rank = HAS_X ? (warp & (kPassWarps / 2 - 1)) : warp;
+    constexpr int kRowsPerWarp = HAS_X ? TN / (kPassWarps / 2) : TN / kPassWarps;
+    const int row0 = (HAS_X ? (warp & (kPassWarps / 2 - 1)) : warp) * kRowsPerWarp;
+    const int kR = omega_role ? 2 : 1;  // the right operand of this warp's product: X or B
+    const int PA = P.pitch[0], PR = P.pitch[kR];
+    const int stA = TN * PA, stR = TN * PR;
+    const bool dbA = P.bufs[0] == 2, dbR = P.bufs[kR] == 2;
+    const bool noneA = P.bufs[0] == 0, noneR = P.bufs[kR] == 0;
 
     double acc[MI][NJ][2];
 #pragma unroll
@@ -404,7 +359,7 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
 #pragma unroll
             for (int j = 0; j < NJ; j++) {
                 const int row = 8 * i + g, col = 8 * j + 2 * q;
-                if (row < P.rA && !(P.debug & 8)) {
+                if (row < P.rA) {
                     double* dst = dst_base + (long long)row * row_pitch + col;
                     if (col < ncols && acc[i][j][0] != 0.0) atomicAdd(dst, acc[i][j][0]);
                     if (col + 1 < ncols && acc[i][j][1] != 0.0) atomicAdd(dst + 1, acc[i][j][1]);
@@ -412,12 +367,41 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
                 acc[i][j][0] = acc[i][j][1] = 0.0;
             }
     };
-    auto flush_psi = [&](long long key) {
-        if (!omega_role) flush(P.psi + key * P.rB, (long long)P.n_mu * P.rB, P.rB);
+    auto flush_psi = [&](long long key) { flush(P.psi + key * P.rB, (long long)P.n_mu * P.rB, P.rB); };
+
+    // Gathered (TABLE / ROWS) sources -> rows [0, n_rows) of stage `stage` of their tiles with
+    // asynchronous global->shared copies (no registers, no waiting): 16-byte chunks when rows are
+    // contiguous and aligned, single doubles (any strides) otherwise.  One commit group per call.
+    auto gather_all = [&](int c, int n_rows, int stage) {
+        if (any_gather && !(P.debug & 4)) {
+#pragma unroll 1
+            for (int k = 0; k < NS; k++) {
+                if (P.bufs[k] != 2) continue;
+                const Source& S = k == 0 ? P.A : (k == 1 ? P.B : P.X);
+                const int units = P.units[k], pitch = P.pitch[k];
+                const int rpi = rows_per_sweep(units, TN);
+                const int prow = tid / units, col = tid - prow * units;
+                if (prow >= rpi) continue;
+                const unsigned long long* fl = s_flat + k * kPiece + c;
+                const int width = P.vec[k] ? 2 : 1;
+                unsigned dst = smem_addr(tiles + P.toff[k] + stage * TN * pitch + prow * pitch + width * col);
+                const unsigned dstep = (unsigned)(rpi * pitch * 8);
+                if (P.vec[k]) {
+                    const double* col_base = S.base + 2 * col;
+                    for (int p = prow; p < n_rows; p += rpi, dst += dstep)
+                        cp_async16(dst, col_base + (long long)fl[p] * S.row_stride);
+                } else {
+                    const double* col_base = S.base + (long long)col * S.col_stride;
+                    for (int p = prow; p < n_rows; p += rpi, dst += dstep)
+                        cp_async8(dst, col_base + (long long)fl[p] * S.row_stride);
+                }
+            }
+        }
+        cp_async_commit();
     };
 
     // ---- work items: contiguous ranges of the sorted order, cut at segment boundaries where
-    // one is near (so a slice of Psi is flushed by one CTA, once), inside long segments otherwise
+    // one is near (so a slice of Psi is mostly flushed by one CTA), inside long segments otherwise
     for (long long item = blockIdx.x; item < P.work_items; item += gridDim.x) {
         __syncthreads();
         if (tid == 0) {
@@ -432,143 +416,202 @@ __global__ void __launch_bounds__(kPassThreads) sparse_pass_kernel(const PassPar
         }
         __syncthreads();
         const long long item_lo = s_bounds[0], item_hi = s_bounds[1];
-        long long cur_key = -1;
-        // (key, id) words of the next piece are prefetched while the current piece is processed
-        unsigned long long w_next[kPiece / kPassThreads];
+        int cur_key = -1;
+        // Staging pipeline, three pieces deep: the (key, id) words of pieces s+1 and s+2 sit in
+        // registers; while piece s is staged, the packed record of every nonzero of piece s+2 and
+        // the table / chain rows of every nonzero of piece s+1 are pulled into L2, so neither the
+        // record reads nor the asynchronous row gathers of a later tile wait on DRAM.
+        constexpr int kU = kPiece / kPassThreads;
+        unsigned long long w0[kU], w1[kU], w2[kU];
 #pragma unroll
-        for (int u = 0; u < kPiece / kPassThreads; u++) {
+        for (int u = 0; u < kU; u++) {
             const long long pos = item_lo + u * kPassThreads + tid;
-            w_next[u] = (P.keyid && pos < item_hi) ? P.keyid[pos] : 0ull;
+            w0[u] = (P.keyid && pos < item_hi) ? P.keyid[pos] : 0ull;
+            w1[u] = (P.keyid && pos + kPiece < item_hi) ? P.keyid[pos + kPiece] : 0ull;
+            w2[u] = (P.keyid && pos + 2 * kPiece < item_hi) ? P.keyid[pos + 2 * kPiece] : 0ull;
+            if (P.recs && pos + kPiece < item_hi)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.recs + (w1[u] & 0xffffffffull) * P.rec_words));
         }
         for (long long s = item_lo; s < item_hi; s += kPiece) {
             const int n_piece = (int)((s + kPiece < item_hi) ? kPiece : item_hi - s);
-            __syncthreads();  // previous piece fully consumed (tiles, staged records, queues)
+            __syncthreads();  // previous piece fully consumed (tiles, staged records)
             // ---- stage the piece: gather value and index rows of every nonzero, fold flat indices
 #pragma unroll
-            for (int u = 0; u < kPiece / kPassThreads; u++) {
+            for (int u = 0; u < kU; u++) {
                 const int i = u * kPassThreads + tid;
                 const bool in = i < n_piece;
                 long long id = s + i;
                 int key = in ? 0 : -1;
                 if (in && P.keyid) {
-                    id = (long long)(w_next[u] & 0xffffffffull);
-                    key = (int)(w_next[u] >> 32);
+                    id = (long long)(w0[u] & 0xffffffffull);
+                    key = (int)(w0[u] >> 32);
                 }
-                const long long npos = s + kPiece + i;
-                w_next[u] = (P.keyid && npos < item_hi) ? P.keyid[npos] : 0ull;
-                // pull the NEXT piece's record into L2 now (its id is already in a register): the
-                // random 32-byte DRAM access then overlaps this piece's compute
-                if (P.recs && npos < item_hi && !(P.debug & 32))
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.recs + (w_next[u] & 0xffffffffull) * P.rec_words));
                 s_key[i] = key;
                 const unsigned* rec = P.recs ? P.recs + id * P.rec_words : nullptr;
                 s_val[i] = in ? (rec ? *reinterpret_cast<const double*>(rec) : P.val[id]) : 0.0;
-                if (P.A.kind != SRC_NONE) s_fa[i] = in ? fold_flat(P.A, rec, id) : 0ull;
-                if (P.B.kind != SRC_NONE) s_fb[i] = in ? fold_flat(P.B, rec, id) : 0ull;
-                if (HAS_X) s_fx[i] = in ? fold_flat(P.X, rec, id) : 0ull;
-            }
-            __syncthreads();
-            int c = 0;
-            if (!(P.debug & 4)) {  // rows of the piece's first tile -> L2
-                const int rows = (n_piece < TN) ? n_piece : TN;
-                if (gatherA) prefetch_rows_l2<TN>(P.A, s_fa, rows);
-                if (gatherB) prefetch_rows_l2<TN>(P.B, s_fb, rows);
-                if (gatherX) prefetch_rows_l2<TN>(P.X, s_fx, rows);
-            }
-            while (c < n_piece) {
-                // ---- run of equal keys starting at c, at most TN long (every warp computes it)
-                int len = 0;
-                const int key0 = s_key[c];
-                {
-                    bool open = true;
-#pragma unroll
-                    for (int t = 0; t < TN / 32; t++) {
-                        const int pos = c + t * 32 + lane;
-                        const bool same = (pos < n_piece) && (s_key[pos] == key0);
-                        const unsigned m = __ballot_sync(0xffffffffu, same);
-                        if (open) {
-                            if (m == 0xffffffffu) len += 32;
-                            else { len += __ffs(~m) - 1; open = false; }
-                        }
+                if (P.A.kind != SRC_NONE) s_flat[i] = in ? fold_flat(P.A, rec, id) : 0ull;
+                if (P.B.kind != SRC_NONE) s_flat[kPiece + i] = in ? fold_flat(P.B, rec, id) : 0ull;
+                if (HAS_X) s_flat[2 * kPiece + i] = in ? fold_flat(P.X, rec, id) : 0ull;
+                // rows of piece s+1 -> L2 (its records were requested one piece ago)
+                const long long pos1 = s + kPiece + i;
+                if (P.pf_any && pos1 < item_hi && !(P.debug & 8)) {
+                    const long long id1 = P.keyid ? (long long)(w1[u] & 0xffffffffull) : pos1;
+                    const unsigned* rec1 = P.recs ? P.recs + id1 * P.rec_words : nullptr;
+#pragma unroll 1
+                    for (int k = 0; k < NS; k++) {
+                        if (!P.pf[k]) continue;
+                        const Source& S = k == 0 ? P.A : (k == 1 ? P.B : P.X);
+                        const double* row = S.base + (long long)fold_flat(S, rec1, id1) * S.row_stride;
+                        const double* last = row + S.r - 1;
+                        for (const double* ln = row; ln < last; ln += 16)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(ln));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(last));
                     }
                 }
-                const int next_c = c + len;
-                // ---- rows of the NEXT tile -> L2 while this tile is generated and accumulated
-                if (next_c < n_piece && !(P.debug & 4)) {
-                    const int rows = (n_piece - next_c < TN) ? n_piece - next_c : TN;
-                    if (gatherA) prefetch_rows_l2<TN>(P.A, s_fa + next_c, rows);
-                    if (gatherB) prefetch_rows_l2<TN>(P.B, s_fb + next_c, rows);
-                    if (gatherX) prefetch_rows_l2<TN>(P.X, s_fx + next_c, rows);
+                // records of piece s+2 -> L2
+                if (P.recs && s + 2 * kPiece + i < item_hi)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.recs + (w2[u] & 0xffffffffull) * P.rec_words));
+                w0[u] = w1[u];
+                w1[u] = w2[u];
+                const long long pos3 = s + 3 * kPiece + i;
+                w2[u] = (P.keyid && pos3 < item_hi) ? P.keyid[pos3] : 0ull;
+            }
+            __syncthreads();
+            gather_all(0, n_piece < TN ? n_piece : TN, 0);  // first tile of the piece -> stage 0
+            int stage = 0;
+            for (int c = 0; c < n_piece; c += TN, stage ^= 1) {
+                const int n_rows = (n_piece - c < TN) ? n_piece - c : TN;
+                // ---- asynchronous gathers of the NEXT tile into the other stage (free since the barrier that ended the previous tile)
+                if (c + TN < n_piece) gather_all(c + TN, (n_piece - c - TN < TN) ? n_piece - c - TN : TN, stage ^ 1);
+                else cp_async_commit();
+                // ---- on-the-fly sources of THIS tile.  A thread owns one column (its salt in a
+                // register) and walks the rows, two per iteration so two independent hash / Horner
+                // chains are in flight.  The central branch of ndtri runs for every lane without a
+                // branch (a diverged warp would issue it anyway); lanes whose uniform may fall in a
+                // tail keep the uniform in the tile and push the slot on the warp's private queue,
+                // which the same warp then drains densely.
+#pragma unroll 1
+                for (int k = 0; k < NS; k++) {
+                    if (P.bufs[k] != 1 || (P.debug & 1)) continue;
+                    const int r = P.units[k], pitch = P.pitch[k];
+                    const int rpi = rows_per_sweep(r, TN);
+                    int p0 = tid / r;
+                    const int col = tid - p0 * r;
+                    const unsigned long long salt = s_salt[64 * k + col];
+                    if (p0 >= rpi) p0 = 1 << 20;  // idle thread: every row test fails
+                    const unsigned long long* fl = s_flat + k * kPiece + c;
+                    const int step = rpi * pitch;
+                    int off0 = P.toff[k] + (p0 < rpi ? p0 : 0) * pitch + col;
+                    int wcount = 0;
+                    for (int base = 0; base < n_rows; base += 2 * rpi) {  // warp-uniform trip count
+                        const int p1 = p0 + rpi, off1 = off0 + step;
+                        const bool v0 = p0 < n_rows, v1 = p1 < n_rows;
+                        const unsigned long long h0 = hash64(fl[v0 ? p0 : 0] + salt);
+                        const unsigned long long h1 = hash64(fl[v1 ? p1 : 0] + salt);
+                        const unsigned hi0 = (unsigned)(h0 >> 32) & 0xFFFFFu, hi1 = (unsigned)(h1 >> 32) & 0xFFFFFu;
+                        const double u0 = __dadd_rn(__hiloint2double((int)(hi0 | 0x3FF00000u), (int)(unsigned)h0), -1.0);
+                        const double u1 = __dadd_rn(__hiloint2double((int)(hi1 | 0x3FF00000u), (int)(unsigned)h1), -1.0);
+                        const bool t0 = v0 && (hi0 - kCentralLo >= kCentralSpan), t1 = v1 && (hi1 - kCentralLo >= kCentralSpan);
+                        const double c0 = ndtri_central(u0), c1 = ndtri_central(u1);
+                        if (v0) tiles[off0] = t0 ? u0 : c0;
+                        if (v1) tiles[off1] = t1 ? u1 : c1;
+                        const unsigned m0 = __ballot_sync(0xffffffffu, t0);
+                        if (t0) wq[wcount + __popc(m0 & lt)] = (unsigned short)off0;
+                        wcount += __popc(m0);
+                        const unsigned m1 = __ballot_sync(0xffffffffu, t1);
+                        if (t1) wq[wcount + __popc(m1 & lt)] = (unsigned short)off1;
+                        wcount += __popc(m1);
+                        p0 += 2 * rpi;
+                        off0 += 2 * step;
+                    }
+                    // the warp's deferred tails, dense over the queue.  The generator pre-filters on the high
+                    // word of the uniform only, so a (rare) entry may belong to the central branch after all.
+                    __syncwarp();
+                    for (int qi = lane; qi < wcount; qi += 32) {
+                        const int off = wq[qi];
+                        const double u = tiles[off];
+                        const int cls = ndtri_class(u);
+                        tiles[off] = (cls == 0) ? ndtri_central(u) : ndtri_tail(u, cls, s_tab);
+                    }
+                    __syncwarp();
                 }
-                if ((long long)key0 != cur_key) {
-                    if (cur_key >= 0) flush_psi(cur_key);
-                    cur_key = key0;
+                cp_async_wait<1>();  // this thread's copies of THIS tile have landed
+                if (n_rows < TN) {
+                    // rows [n_rows, TN) of a partial tile must not hold stale non-finite data (they are multiplied by v = 0)
+#pragma unroll 1
+                    for (int k = 0; k < NS; k++) {
+                        if (P.bufs[k] == 0) continue;
+                        double* t = tiles + P.toff[k] + (P.bufs[k] == 2 ? stage * TN * P.pitch[k] : 0);
+                        for (int e = n_rows * P.pitch[k] + tid; e < TN * P.pitch[k]; e += kPassThreads) t[e] = 0.0;
+                    }
                 }
-                double* At_c = At;
-                double* Bt_c = Bt;
-                double* Xt_c = Xt;
-                // ---- on-the-fly sources, then this warp's deferred tails
-                int wcount = 0;
-                if (P.A.kind == SRC_GAUSS)
-                    fill_gauss<TN>(P.A, P.rpiA, P.magicA, 0, At_c, PA, len, s_fa + c, s_salt, wq, wcount, P.debug, At_c, Bt_c, Xt_c, s_tab);
-                if (P.B.kind == SRC_GAUSS)
-                    fill_gauss<TN>(P.B, P.rpiB, P.magicB, 1, Bt_c, PB, len, s_fb + c, s_salt + 64, wq, wcount, P.debug, At_c, Bt_c, Xt_c, s_tab);
-                if (HAS_X && P.X.kind == SRC_GAUSS)
-                    fill_gauss<TN>(P.X, P.rpiX, P.magicX, 2, Xt_c, PX, len, s_fx + c, s_salt + 128, wq, wcount, P.debug, At_c, Bt_c, Xt_c, s_tab);
-                drain_tail_queue(At_c, Bt_c, Xt_c, wq, wcount, s_tab);
                 __syncthreads();
-                // ---- accumulate: k-chunks of 4 nonzeros; A fragment scaled by the value.  Fragments of
-                // generated sources come from the shared-memory tile, those of gathered sources
-                // straight from global memory (L2-resident thanks to the prefetch above).
+                // ---- accumulate: k-chunks of 4 rows; the A fragment is scaled by the value
                 if (!(P.debug & 2)) {
-                    const bool r_gather = omega_role ? gatherX : gatherB;
-                    const Source& RS = omega_role ? P.X : P.B;
-                    const double* Rt = omega_role ? Xt_c : Bt_c;
-                    const int PR = omega_role ? PX : PB;
-                    const unsigned long long* s_fr = omega_role ? s_fx : s_fb;
-                    const int rR_cols = omega_role ? P.rX : P.rB;
-                    for (int ch = role_rank; ch * 4 < len; ch += role_warps) {
-                        const int p0 = ch * 4 + q;
-                        const double v = (p0 < len) ? s_val[c + p0] : 0.0;
-                        const int pr = (p0 < len) ? c + p0 : c;  // rows past the run read a valid row (scaled by v = 0)
+                    const double* At = tiles + P.toff[0] + (dbA ? stage * stA : 0);
+                    const double* Rt = tiles + P.toff[kR] + (dbR ? stage * stR : 0);
+#pragma unroll 2
+                    for (int ch = 0; ch < kRowsPerWarp / 4; ch++) {
+                        const int rbase = row0 + 4 * ch;
+                        if (rbase >= n_rows) break;  // warp-uniform
+                        const int p = rbase + q;
+                        const double v = s_val[c + p];  // 0 past the piece
                         double a[MI], b[NJ];
-                        if (gatherA) {
-                            const double* row = P.A.base + (long long)s_fa[pr] * P.A.row_stride;
-#pragma unroll
-                            for (int i = 0; i < MI; i++)
-                                a[i] = (8 * i + g < P.rA && !(P.debug & 4)) ? __ldg(row + (long long)(8 * i + g) * P.A.col_stride) * v : 0.0;
-                        } else if (P.A.kind == SRC_NONE) {  // Psi_0: the left factor is the scalar 1
+                        if (noneA) {  // Psi_0: the left factor is the scalar 1
 #pragma unroll
                             for (int i = 0; i < MI; i++) a[i] = (i == 0 && g == 0) ? v : 0.0;
                         } else {
 #pragma unroll
-                            for (int i = 0; i < MI; i++) a[i] = At_c[p0 * PA + 8 * i + g] * v;
+                            for (int i = 0; i < MI; i++) a[i] = At[p * PA + 8 * i + g] * v;
                         }
-                        if (r_gather) {
-                            const double* row = RS.base + (long long)s_fr[pr] * RS.row_stride;
-#pragma unroll
-                            for (int j = 0; j < NJ; j++)
-                                b[j] = (8 * j + g < rR_cols && !(P.debug & 4)) ? __ldg(row + (long long)(8 * j + g) * RS.col_stride) : 0.0;
-                        } else if (RS.kind == SRC_NONE) {  // Psi_{d-1}: the right factor is the scalar 1
+                        if (noneR) {  // Psi_{d-1}: the right factor is the scalar 1
 #pragma unroll
                             for (int j = 0; j < NJ; j++) b[j] = (j == 0 && g == 0) ? 1.0 : 0.0;
                         } else {
 #pragma unroll
-                            for (int j = 0; j < NJ; j++) b[j] = Rt[p0 * PR + 8 * j + g];
+                            for (int j = 0; j < NJ; j++) b[j] = Rt[p * PR + 8 * j + g];
                         }
+                        bool plain = omega_role;
+                        int key = 0;
+                        if (!omega_role) {
+                            key = s_key[c + p];  // -1 past the piece
+                            plain = __all_sync(0xffffffffu, key == cur_key);
+                        }
+                        if (plain) {
 #pragma unroll
-                        for (int i = 0; i < MI; i++)
+                            for (int i = 0; i < MI; i++)
 #pragma unroll
-                            for (int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                                for (int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                        } else {
+                            // the chunk starts a new segment or straddles segment boundaries: one MMA round per run of equal keys
+                            int start = 0;
+                            while (start < 4) {
+                                const int kcur = __shfl_sync(0xffffffffu, key, start);  // lane `start` holds row rbase + start
+                                if (kcur < 0) break;
+                                if (kcur != cur_key) {
+                                    if (cur_key >= 0) flush_psi(cur_key);
+                                    cur_key = kcur;
+                                }
+                                const bool mine = (q >= start) && (key == kcur);
+                                const unsigned diff = __ballot_sync(0xffffffffu, (q > start) && (key != kcur)) & 0xFu;
+#pragma unroll
+                                for (int i = 0; i < MI; i++) {
+                                    const double am = mine ? a[i] : 0.0;
+#pragma unroll
+                                    for (int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], am, b[j]);
+                                }
+                                start = diff ? (__ffs(diff) - 1) : 4;
+                            }
+                        }
                     }
                 }
                 __syncthreads();
-                c = next_c;
             }
         }
-        if (cur_key >= 0) flush_psi(cur_key);
+        if (!omega_role && cur_key >= 0) flush_psi(cur_key);
     }
     if (omega_role) flush(P.omega, P.rX, P.rX);
+    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------ TT-DRM chain step, bucketed
@@ -705,28 +748,45 @@ static int launch_chain(ttsk_ctx* ctx, ChainParams& C, cudaStream_t st) {
     }
 }
 
+// per-source tile plan for a tile height `tn`; returns the kernel's shared-memory bytes (must match its carve-up)
+template <int MI, int NJ, bool HAS_X>
+static size_t plan_pass(PassParams& P, int tn) {
+    const Source* src[3] = {&P.A, &P.B, &P.X};
+    const int piece = piece_for(tn);
+    P.pf_any = 0;
+    const int pitches[3] = {tile_pitch(MI), tile_pitch(NJ), tile_pitch(NJ)};
+    int off = 0, max_rows = 1;
+    for (int k = 0; k < 3; k++) {
+        const Source& S = *src[k];
+        P.pitch[k] = pitches[k];
+        P.bufs[k] = 0; P.units[k] = 1; P.vec[k] = 0; P.toff[k] = off; P.pf[k] = 0;
+        if ((k == 2 && !HAS_X) || S.kind == SRC_NONE) continue;
+        if (S.kind == SRC_GAUSS) {
+            P.bufs[k] = 1;
+            P.units[k] = S.r;
+            const int rpi = rows_per_sweep(S.r, tn);
+            max_rows = std::max(max_rows, (tn + rpi - 1) / rpi);
+        } else {
+            P.bufs[k] = 2;
+            const bool aligned = S.col_stride == 1 && (S.r % 2 == 0) && (S.row_stride % 2 == 0) &&
+                                 (reinterpret_cast<uintptr_t>(S.base) % 16 == 0);
+            P.vec[k] = aligned ? 1 : 0;
+            P.units[k] = aligned ? S.r / 2 : S.r;
+            // arrays that cannot stay L2-resident are prefetched a piece ahead (contiguous rows only)
+            P.pf[k] = (S.col_stride == 1 && (S.span_bytes == 0 || S.span_bytes > ((long long)16 << 20))) ? 1 : 0;
+            P.pf_any |= P.pf[k];
+        }
+        off += P.bufs[k] * tn * P.pitch[k];
+    }
+    P.queue_cap = (32 * (max_rows + 1) + 7) & ~7;  // every lane of a warp may push one slot per row pair member
+    return (size_t)kGaussTabEntries * 16 + (size_t)piece * 8 * 4 + 192 * 8 + (size_t)piece * 4 + 16 + (size_t)off * 8 +
+           (size_t)kPassWarps * P.queue_cap * 2 + 64;
+}
+
 template <int MI, int NJ, bool HAS_X, int TN>
 static int launch_pass_t(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     auto kern = sparse_pass_kernel<MI, NJ, HAS_X, TN>;
-    auto gathered = [](const Source& S) { return S.kind == SRC_ROWS || S.kind == SRC_TABLE; };
-    P.pitchA = tile_pitch(MI);
-    P.pitchB = tile_pitch(NJ);
-    P.pitchX = tile_pitch(NJ);
-    P.bufsA = P.A.kind == SRC_GAUSS ? 1 : 0;
-    P.bufsB = P.B.kind == SRC_GAUSS ? 1 : 0;
-    P.bufsX = (HAS_X && P.X.kind == SRC_GAUSS) ? 1 : 0;
-    auto magic = [](int r) { return (((unsigned long long)1 << 32) + (unsigned)r - 1) / (unsigned)r; };
-    P.magicA = magic(P.A.r > 0 ? P.A.r : 1);
-    P.magicB = magic(P.B.r > 0 ? P.B.r : 1);
-    P.magicX = magic(P.X.r > 0 ? P.X.r : 1);
-    P.rpiA = kPassThreads / (P.A.r > 0 ? P.A.r : 1);
-    P.rpiB = kPassThreads / (P.B.r > 0 ? P.B.r : 1);
-    P.rpiX = kPassThreads / (P.X.r > 0 ? P.X.r : 1);
-    P.queue_cap_w = kQueueCap;
-    const size_t tile_doubles = (size_t)P.bufsA * (TN + 1) * P.pitchA + (size_t)P.bufsB * (TN + 1) * P.pitchB +
-                                (size_t)P.bufsX * (TN + 1) * P.pitchX;
-    const size_t smem = 128 * 16 + (size_t)kPiece * 8 * 4 + 192 * 8 + tile_doubles * 8 + (size_t)kPiece * 4 +
-                        (size_t)(kPassWarps * P.queue_cap_w + 2) * 4 + 64;
+    const size_t smem = plan_pass<MI, NJ, HAS_X>(P, TN);
     P.smem_bytes = (int)smem;
     TTSK_ARG(smem <= 227 * 1024, "sparse pass: shared-memory plan exceeds 227 KB (ranks too large)");
     TTSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -737,20 +797,33 @@ static int launch_pass_t(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     long long grid = (long long)ctx->sm_count * per_sm;
     // ~8 work items per CTA for balance, none shorter than a few pieces
     long long items = grid * 8;
-    const long long min_len = 8 * kPiece;
+    const long long min_len = 8 * piece_for(TN);
     if (items * min_len > P.nnz) items = (P.nnz + min_len - 1) / min_len;
     if (items < 1) items = 1;
-    P.debug = getenv("TTSK_ABLATE") ? atoi(getenv("TTSK_ABLATE")) : 0;
     P.work_items = items;
     P.item_len = (P.nnz + items - 1) / items;
+    P.debug = getenv("TTSK_ABLATE") ? atoi(getenv("TTSK_ABLATE")) : 0;
     if (grid > items) grid = items;
     if (grid < 1) grid = 1;
     if (getenv("TTSK_DEBUG"))
-        fprintf(stderr, "[ttsk] pass MI=%d NJ=%d X=%d TN=%d smem=%zu ctas/sm=%d grid=%lld items=%lld\n", MI, NJ, (int)HAS_X, TN,
-                smem, per_sm, grid, items);
+        fprintf(stderr, "[ttsk] pass MI=%d NJ=%d X=%d TN=%d smem=%zu ctas/sm=%d grid=%lld items=%lld bufs=%d%d%d vec=%d%d%d\n", MI, NJ,
+                (int)HAS_X, TN, smem, per_sm, grid, items, P.bufs[0], P.bufs[1], P.bufs[2], P.vec[0], P.vec[1], P.vec[2]);
     kern<<<(unsigned)grid, kPassThreads, smem, st>>>(P);
     TTSK_LAUNCHED(ctx);
     return TTSK_OK;
+}
+
+// tile height: 128 rows when at least two CTAs of that size fit one SM, else 64 (gathered sources are double-buffered)
+template <int MI, int NJ, bool HAS_X>
+static int launch_pass_tn(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
+    static const int forced = getenv("TTSK_TN") ? atoi(getenv("TTSK_TN")) : 0;
+    int tn = (2 * (plan_pass<MI, NJ, HAS_X>(P, 128) + 1024) <= 227 * 1024) ? 128 : 64;
+    if (forced == 64 || forced == 128) tn = forced;
+    if (forced == 256 && P.bufs[0] != 2 && P.bufs[1] != 2 && P.bufs[2] != 2 &&
+        plan_pass<MI, NJ, HAS_X>(P, 256) + 1024 <= 227 * 1024)
+        tn = 256;  // generated sources only: taller tiles quantise the generator and its tail queue better
+    if (tn == 256) return launch_pass_t<MI, NJ, HAS_X, 256>(ctx, P, st);
+    return (tn == 64) ? launch_pass_t<MI, NJ, HAS_X, 64>(ctx, P, st) : launch_pass_t<MI, NJ, HAS_X, 128>(ctx, P, st);
 }
 
 template <bool HAS_X>
@@ -758,9 +831,7 @@ static int launch_pass_x(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
     const int mi = (P.rA + 7) / 8;
     const int nj = (std::max(P.rB, HAS_X ? P.rX : 1) + 7) / 8;
     TTSK_ARG(mi <= 8 && nj <= 8, "sparse pass: DRM rank above 64 is not supported by the fused kernel");
-#define TTSK_PASS(MI_, NJ_)                                                            \
-    return (tn == 64) ? launch_pass_t<MI_, NJ_, HAS_X, 64>(ctx, P, st) : launch_pass_t<MI_, NJ_, HAS_X, 128>(ctx, P, st)
-    static const int tn = getenv("TTSK_TN") ? atoi(getenv("TTSK_TN")) : 128;
+#define TTSK_PASS(MI_, NJ_) return launch_pass_tn<MI_, NJ_, HAS_X>(ctx, P, st)
     const int MIr = mi <= 1 ? 1 : (mi <= 3 ? 3 : (mi <= 5 ? 5 : 8));
     const int NJr = nj <= 1 ? 1 : (nj <= 3 ? 3 : (nj <= 5 ? 5 : 8));
     switch (MIr * 10 + NJr) {
@@ -1123,6 +1194,7 @@ static int build_plan(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* shape
                         S.base = tab;
                         S.row_stride = S.r;
                         S.col_stride = 1;
+                        S.span_bytes = rows * S.r * 8;
                     }
                 }
             } else {
@@ -1278,6 +1350,18 @@ extern "C" int ttsk_last_kernel_ms(ttsk_ctx* ctx, double* ms_total, double* ms_d
         sum += p;
     }
     if (ms_dominant) *ms_dominant = sum;
+    return TTSK_OK;
+}
+
+extern "C" int ttsk_last_pass_ms(ttsk_ctx* ctx, double* ms, int cap, int* n_out) {
+    TTSK_ARG(ctx != nullptr && n_out != nullptr && (cap == 0 || ms != nullptr), "last_pass_ms");
+    TTSK_CUDA(cudaEventSynchronize(ctx->ev_t1));
+    *n_out = ctx->n_pass_events;
+    for (int i = 0; i < ctx->n_pass_events && i < cap; i++) {
+        float p = 0.f;
+        TTSK_CUDA(cudaEventElapsedTime(&p, ctx->ev_pass[2 * i], ctx->ev_pass[2 * i + 1]));
+        ms[i] = p;
+    }
     return TTSK_OK;
 }
 
