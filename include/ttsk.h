@@ -62,6 +62,8 @@ int64_t ttsk_launch_count(ttsk_ctx *ctx);
 int ttsk_last_kernel_ms(ttsk_ctx *ctx, double *ms_total, double *ms_dominant);
 /* Per-launch milliseconds of the dominant (mode pass) kernel in that call: fills ms[0..min(cap, n)) and returns n in *n_out. */
 int ttsk_last_pass_ms(ttsk_ctx *ctx, double *ms, int cap, int *n_out);
+/* Number of sparse mode passes this context ran in the segment-GEMM form (small trailing prefix tables). */
+int64_t ttsk_sg_pass_count(ttsk_ctx *ctx);
 
 /* ---------------------------------------------------------------- lazy Gaussian DRM
  * Replaces inds_to_normal(indices, shape, rank_min, rank_max, seed)

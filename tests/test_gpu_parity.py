@@ -202,6 +202,30 @@ def test_sparse_c4_shape_vs_oracle(oracle_lib, kinds, nnz):
     assert [p.shape for p in stt.Psi_cores] == [(1, 10000, 40), (20, 10000, 40), (20, 10000, 40), (20, 500, 1)]
 
 
+@pytest.mark.parametrize("rl,rr", [((20, 20, 20), (40, 40, 40)), ((5, 7, 3), (6, 9, 4))])
+def test_sparse_segment_gemm_form_vs_oracle(oracle_lib, rl, rr):
+    """Small trailing modes and long segments: mode 2 runs in the segment-GEMM form (T_j^T R tables once per
+    segment instead of per-nonzero gathers + MMAs); same oracle, same tolerance."""
+    from oracle.sketch_oracle import Drm
+    from tt_sketch import _backend as be
+    from tt_sketch.sketch import stream_sketch
+
+    shape, nnz = (3000, 3000, 16, 30), 120000
+    _, idx, val = _c4_like(nnz, seed=7, shape=shape)
+    idx[2, :5000] = 3   # one long segment next to ordinary ones
+    oL = Drm("gauss", False, shape, (0,) * 3, rl, 11)
+    oR = Drm("gauss", True, shape, (0,) * 3, rr, 12)
+    desc = ("sparse", shape, idx, val)
+    Psi, Om = oracle_lib.general_sketch(desc, oL, oR, "streaming", fast_sparse=True)
+    before = be.lib().ttsk_sg_pass_count(be.ctx())
+    stt = stream_sketch(make_tensor(desc), rl, rr, left_drm=make_drm(oL), right_drm=make_drm(oR))
+    assert be.lib().ttsk_sg_pass_count(be.ctx()) > before, "segment-GEMM form was not taken"
+    for a, b in zip(stt.Psi_cores, Psi):
+        assert rel_err(a, b) < TOL
+    for a, b in zip(stt.Omega_mats, Om):
+        assert rel_err(a, b) < TOL
+
+
 def test_sparse_duplicates_empty_slices_and_ragged_segments(oracle_lib):
     """Edge cases: duplicate coordinates (summed), slices with no nonzero, one huge segment next
     to singletons, nnz not a multiple of the tile, a single nonzero."""

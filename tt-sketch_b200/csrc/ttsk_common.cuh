@@ -54,6 +54,7 @@ struct ttsk_ctx {
     int device = 0;
     int sm_count = 148;
     int64_t launches = 0;
+    int64_t sg_passes = 0;  // mode passes that ran in the segment-GEMM form
     // workspace arena
     char* ws = nullptr;
     int64_t ws_bytes = 0;

@@ -52,6 +52,7 @@ SIGNATURES = {
     "ttsk_launch_count": (c_int64, [c_void_p]),
     "ttsk_last_kernel_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "ttsk_last_pass_ms": (c_int, [c_void_p, POINTER(c_double), c_int, POINTER(c_int)]),
+    "ttsk_sg_pass_count": (c_int64, [c_void_p]),
     "ttsk_lazy_gaussian": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, POINTER(c_int64), c_int, c_int,
                                    c_uint64, c_void_p, c_void_p]),
     "ttsk_selftest_div": (c_int, [c_void_p, c_int64, c_uint64, POINTER(c_uint64)]),
