@@ -67,7 +67,7 @@ def make_coo(nnz, lo, hi):
 def measured_traffic(nnz):
     """dram__bytes_read.sum + dram__bytes_write.sum of the pass kernel, per launch, from the committed
     ncu --set full capture of this workload (profiles/r01_pass_traffic_1e8nnz.json); None for other sizes."""
-    path = os.path.join(ROOT, "profiles", "r01_pass_traffic_1e8nnz.json")
+    path = os.path.join(ROOT, "profiles", "r01_pass_traffic_1e8nnz.json")  # rewritten by tools/ncu_summary.py
     try:
         d = json.load(open(path))
         if int(d["nnz"]) == int(nnz):
@@ -360,7 +360,7 @@ def main():
                          "launches_per_step": n_pass,
                          "note": "algorithmic 40 B/nnz over the d=4 mode passes (10 B/nnz per launch) / summed pass "
                                  "time of the last step; the kernel is FP64-issue-bound (bit-exact ndtri), see "
-                                 "fp64_pipe and DESIGN.md section 5"},
+                                 "fp64_pipe and DESIGN.md section 3"},
             "fp64_pipe": fp64_model(n_loc, pass_kernels_ms),
             "kernel_ms": {"pass_kernels_last_step": pass_kernels_ms, "all_kernels_last_step": step_kernels_ms,
                           "per_pass_last_step": per_pass_ms},
@@ -388,7 +388,9 @@ def fp64_model(n_loc, pass_ms):
      over the measured DFMA issue rate of this B200 (tools/fp64_microbench)."""
     otf_variates = 20 + 20 + 40            # L_1, L_2, R_0 (L_0, R_1, R_2 come from prefix tables)
     per_variate = 0.73 * 42 + 0.27 * 112   # central / tail branch FP64 instructions
-    mma_fma = 8 * 40 + 2 * 24 * 40 + 24 * 40 + 24 * 8  # Psi_0, Psi_1+Psi_2, Omega_1, Psi_3 (8x8x4 padded tiles)
+    # Psi_0 and Psi_1 as padded 8x8x4 MMA tiles, Psi_3 likewise; Psi_2 / Omega_1 run in the segment-GEMM form:
+    # 20 multiplies + 20 adds per nonzero (the per-segment GEMMs are negligible)
+    mma_fma = 8 * 40 + 24 * 40 + 24 * 8 + 2 * 20
     per_nnz = otf_variates * per_variate + mma_fma
     peak = 1.68e13
     ach = per_nnz * n_loc / (pass_ms * 1e-3) if pass_ms > 0 else 0.0
