@@ -356,7 +356,7 @@ def main():
             "config": config_dict(nnz, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(nnz) if world == 1 else None, "peak_source": which,
-                         "kernel": "ttsk::sparse_pass_kernel", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_NNZ * n_loc / n_pass,
+                         "kernel": "ttsk::sparse_pass_kernel / ttsk::sparse_sg_kernel (one launch per mode)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_NNZ * n_loc / n_pass,
                          "launches_per_step": n_pass,
                          "note": "algorithmic 40 B/nnz over the d=4 mode passes (10 B/nnz per launch) / summed pass "
                                  "time of the last step; the kernel is FP64-issue-bound (bit-exact ndtri), see "
