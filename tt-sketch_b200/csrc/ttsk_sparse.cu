@@ -35,66 +35,9 @@ int gauss_table_launch(ttsk_ctx* ctx, int64_t rows, int rank_min, int rank, uint
                        cudaStream_t st);
 void wrapped_strides(const int64_t* shape, int k, long long* strides);
 
-enum { SRC_NONE = 0, SRC_GAUSS = 1, SRC_ROWS = 2, SRC_TABLE = 3 };
-
-struct Source {
-    int kind;
-    int r;         // columns produced
-    int k;         // modes in the flat index (GAUSS / TABLE)
-    int rank_min;  // GAUSS: first column of the infinite matrix
-    int modes[TTSK_MAX_ORDER];
-    long long strides[TTSK_MAX_ORDER];
-    unsigned long long seed;
-    const double* base;  // ROWS / TABLE: element (q, a) at base[q*row_stride + a*col_stride]
-    long long row_stride, col_stride;
-    long long span_bytes;  // ROWS / TABLE: size of the gathered array (0: unknown); small arrays live in L2 and are not prefetched
-};
-
-// The bucket scatter writes ONE packed word per nonzero in sorted order: (key << 32) | id with
-// key = i_mu and id = position in the chunk.  The pass kernel streams this array (coalesced)
-// and gathers the value / index rows of each nonzero itself: those random 8-byte reads run on
-// the otherwise idle memory pipes of an FP64-bound kernel instead of in a separate
-// bandwidth-bound sort kernel.
-struct ScatterIdx {
-    const long long* idx[TTSK_MAX_ORDER];
-};
-
-struct ScatterParams {
-    long long nnz;
-    const long long* key_idx;
-    int* cursor;
-    unsigned long long* keyid;
-};
-
-struct PassParams {
-    long long nnz;
-    long long n_mu;
-    const unsigned long long* keyid;  // sorted (key << 32 | id); nullptr: identity order, key 0
-    const unsigned* recs;    // packed records [val(2 words) | int32 idx[d] | pad], rec_words each; or nullptr
-    int rec_words;
-    const double* val;       // used when recs == nullptr (operator-level passes need no indices)
-    Source A, B, X;
-    int rA, rB, rX;  // logical tile widths (1 for SRC_NONE)
-    double* psi;     // (rA, n_mu, rB)
-    double* omega;   // (rA, rX), only with X
-    // shared-memory plan (host computed), per source s = 0 (A), 1 (B), 2 (X)
-    int pitch[3];    // row pitch of the tile in doubles
-    int bufs[3];     // 0 absent source, 1 generated by the consumers, 2 gathered by the producer (asynchronous copies)
-    int units[3];    // work units per row: columns (generated), 16-byte chunks or single doubles (gathered)
-    int vec[3];      // gathered: 1 = contiguous 16-byte-aligned rows (16-byte copies)
-    int soff[3];     // gathered: byte offset of the source's rows inside a stage
-    int goff[3];     // generated: offset of the source's tile in the generated-tile area (doubles)
-    int gen_doubles; // size of the generated-tile area
-    int nstages, stage_bytes;
-    long long smul[3][6];  // per source and mode: stride of the mode in the source's flat index (0: unused)
-    int fold_static;       // records are 32 bytes (d <= 6): flat indices as fixed dot products
-    int sg_mode, sg_S;     // segment-GEMM form: the pass mode, rows of the B table
-    int queue_cap;   // 16-bit tail-queue slots per consumer warp (worst case of one source's tile: no overflow possible)
-    int smem_bytes;
-    const int* offs;             // segment starts in the sorted order (n_mu + 1), or nullptr
-    long long work_items, item_len;
-    int debug;  // profiling switches (TTSK_ABLATE), tested once per tile: 1 no generation, 2 no MMA, 4 no row gathers, 8 no L2 row prefetch
-};
+}  // namespace ttsk
+#include "ttsk_sparse_pass.cuh"
+namespace ttsk {
 
 // ------------------------------------------------------------------ bucketing (counting sort)
 __global__ void hist_kernel(const long long* __restrict__ idx, long long nnz, int* __restrict__ hist) {
@@ -175,16 +118,6 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ hist
     if (threadIdx.x == 0) offs[n] = s_carry;
 }
 
-// flat index of one source from a packed record (int32 indices start at word 2); the record is a
-// single 32-byte sector, so after the value has been read these loads hit L1
-__device__ __forceinline__ unsigned long long fold_flat(const Source& f, const unsigned* __restrict__ rec,
-                                                        long long id) {
-    if (f.kind == SRC_ROWS) return (unsigned long long)id;
-    unsigned long long flat = 0;
-    for (int i = 0; i < f.k; i++)
-        flat += (unsigned long long)rec[2 + f.modes[i]] * (unsigned long long)f.strides[i];
-    return flat;
-}
 
 // Pack the chunk's COO arrays (SoA, int64 indices) into one sector-sized record per nonzero so a
 // mode pass fetches a nonzero with ONE random 32-byte access instead of d+1 of them.
@@ -262,516 +195,6 @@ __global__ void __launch_bounds__(256) ttdrm_step_kernel(long long nnz, const lo
         }
         v_out[e] = s;
     }
-}
-
-// ------------------------------------------------------------------ the mode pass
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-constexpr int kConsumerWarps = 8;
-__host__ __device__ constexpr int pass_threads(int np) { return 32 * (kConsumerWarps + np); }  // + np producer warps
-constexpr int kMaxStages = 8;
-// row pitch (doubles) of a tile with `tiles8` 8-wide MMA column tiles: == 8 (mod 16) so the
-// MMA fragment loads (4 rows x 8 columns per warp) are bank-conflict free
-__host__ __device__ constexpr int tile_pitch(int tiles8) { return 8 * tiles8 + ((tiles8 % 2 == 0) ? 8 : 0); }
-
-__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
-#if 1  // .cg (L1 bypass) measured 6 % faster than .ca on the gather-bound mode
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-#else
-    // through L1 (.ca): the lanes of one copy instruction that share a 32-byte sector are merged into one request
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(b)) : "memory");
-}
-// arrive on the barrier once all cp.async copies this thread has issued so far have landed
-__device__ __forceinline__ void mbar_arrive_on_copies(unsigned long long* b) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(b)) : "memory");
-}
-// try_wait with a suspend-time hint parks the warp in hardware until the phase completes (or the
-// hint expires), so a waiting warp does not burn the issue slots the generating warps need
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
-    const unsigned addr = smem_addr(b);
-    unsigned done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}" : "=r"(done) : "r"(addr), "r"(parity), "r"(200000u) : "memory");
-    } while (!done);
-}
-// a producer that is ahead of the ring polls a release counter: back off up to 2 us between looks
-__device__ __forceinline__ void wait_released(volatile unsigned* counter, unsigned need, unsigned max_ns) {
-    unsigned ns = 64;
-    while (*counter < need) {
-        __nanosleep(ns);
-        if (ns < max_ns) ns *= 2;
-    }
-    __threadfence_block();
-}
-__device__ __forceinline__ void named_barrier(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-// high 20 mantissa bits of a uniform that may lie in a tail of ndtri: u <= exp(-2) needs
-// hi <= 141909, u > 1 - exp(-2) needs hi >= 906666 (conservative by one word each side)
-constexpr unsigned kCentralLo = 141910u, kCentralSpan = 906666u - 141910u;
-
-// first sorted position >= x that starts a segment, if it is within `slack` of x; else x
-__device__ __forceinline__ long long snap_to_segment(const int* __restrict__ offs, long long n_mu, long long x,
-                                                     long long slack) {
-    long long lo = 0, hi = n_mu;  // offs[0..n_mu], offs[n_mu] = nnz
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if ((long long)offs[mid] < x) lo = mid + 1; else hi = mid;
-    }
-    const long long b = offs[lo];
-    return (b - x <= slack) ? b : x;
-}
-
-// A stage of the ring is one tile of TN sorted positions:
-//   [int n_rows | pad to 16 B][double val[TN]][u64 flat[3][TN]][int key[TN]][rows of the gathered sources ...]
-template <int TN>
-struct StageView {
-    unsigned char* base;
-    __device__ __forceinline__ int* hdr() const { return reinterpret_cast<int*>(base); }
-    __device__ __forceinline__ double* val() const { return reinterpret_cast<double*>(base + 16); }
-    __device__ __forceinline__ unsigned long long* flat(int k) const {
-        return reinterpret_cast<unsigned long long*>(base + 16 + TN * 8) + k * TN;
-    }
-    __device__ __forceinline__ int* key() const { return reinterpret_cast<int*>(base + 16 + TN * 8 * 4); }
-    __device__ __forceinline__ double* rows(int byte_off) const { return reinterpret_cast<double*>(base + byte_off); }
-};
-__host__ __device__ constexpr int stage_header_bytes(int tn) { return 16 + tn * 8 * 4 + tn * 4; }  // multiple of 16
-
-// MI/NJ: 8x8 MMA tiles covering rA / max(rB, rX).  TN: rows of a tile.  CH: independent
-// generator chains per lane.  NP: producer warps.
-//
-// Warp-specialised, persistent.  The PRODUCER warps walk the CTA's work items (contiguous ranges
-// of the sorted order) tile by tile (producer j takes every NP-th tile of the CTA's tile stream,
-// so the latencies of NP tiles overlap): a producer reads the (key, id) words and the packed record of every
-// nonzero (records are pulled into L2 two tiles ahead), folds the flat index of every source,
-// and launches asynchronous global->shared copies of the table / chain rows the tile needs; the
-// stage's `full` mbarrier completes when the copies have landed.  The eight CONSUMER warps never
-// meet at a CTA barrier: each owns TN/8 rows of every tile (TN/4 rows per pair of warps with
-// HAS_X: warp w accumulates Psi = (v At)^T Bt, warp w+4 Omega = (v At)^T Xt for the same rows),
-// generates the on-the-fly Gaussian entries of ITS rows, drains its own tail queue, multiplies,
-// and releases the stage through the `empty` mbarrier.  Psi accumulators are flushed with FP64
-// atomics whenever the key (slice index) of the warp's rows changes.
-template <int MI, int NJ, bool HAS_X, int TN, int CH, int NP>
-__global__ void __launch_bounds__(pass_threads(NP), (NP == 1 && MI * NJ <= 5) ? 3 : ((NP == 1 && MI * NJ <= 15) ? 2 : 1))
-    sparse_pass_kernel(const PassParams P) {
-    constexpr int kPassThreads = pass_threads(NP);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* s_tab = reinterpret_cast<double2*>(smem_raw);  // log table + tail coefficients
-    unsigned long long* s_salt = reinterpret_cast<unsigned long long*>(s_tab + kGaussTabEntries);  // [3][64]
-    unsigned long long* bars = s_salt + 192;  // full mbarriers [kMaxStages], then the stages' release counters
-    unsigned char* stages = reinterpret_cast<unsigned char*>(bars + 2 * kMaxStages);
-    double* gtiles = reinterpret_cast<double*>(stages + (size_t)P.nstages * P.stage_bytes);  // generated tiles
-    unsigned short* s_queue = reinterpret_cast<unsigned short*>(gtiles + P.gen_doubles);    // [kConsumerWarps][queue_cap]
-    constexpr int NS = HAS_X ? 3 : 2;
-    const int NST = P.nstages;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    load_logtab(s_tab);
-    for (int i = tid; i < P.gen_doubles; i += kPassThreads) gtiles[i] = 0.0;
-    for (int i = tid; i < NST * P.stage_bytes / 8; i += kPassThreads) reinterpret_cast<double*>(stages)[i] = 0.0;
-    if (tid < 64) {
-        if (P.A.kind == SRC_GAUSS && tid < P.A.r) s_salt[tid] = hash64((unsigned long long)(P.A.rank_min + tid)) + P.A.seed;
-        if (P.B.kind == SRC_GAUSS && tid < P.B.r) s_salt[64 + tid] = hash64((unsigned long long)(P.B.rank_min + tid)) + P.B.seed;
-        if (HAS_X && P.X.kind == SRC_GAUSS && tid < P.X.r) s_salt[128 + tid] = hash64((unsigned long long)(P.X.rank_min + tid)) + P.X.seed;
-    }
-    if (tid == 0) {
-        for (int s = 0; s < NST; s++) {
-            mbar_init(&bars[s], 64);  // 32 copy-completion arrives + 32 plain arrives of the producer
-            reinterpret_cast<unsigned*>(bars + kMaxStages)[s] = 0u;  // release counter of the stage
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();  // the only CTA-wide barrier
-
-    if (warp >= kConsumerWarps) {
-        // =========================================================== producers
-        constexpr int kU = TN / 32;
-        const int pw = warp - kConsumerWarps;
-        constexpr int np = NP;
-        long long n_base = 0;  // index of the item's first tile in the CTA's tile stream
-        // A stage may be refilled once all consumer warps have released its previous tile.  Releases
-        // are counted (not phase-parity tracked) because several producers wait on the same stage
-        // for different revolutions of the ring.
-        volatile unsigned* released = reinterpret_cast<volatile unsigned*>(bars + kMaxStages);
-        auto acquire = [&](long long n) -> StageView<TN> {
-            const int s = (int)(n % NST);
-            const unsigned need = (unsigned)(n / NST) * kConsumerWarps;
-            wait_released(released + s, need, NP > 1 ? 64u : 2048u);  // gather-bound passes: producers are the critical path
-            return StageView<TN>{stages + (size_t)s * P.stage_bytes};
-        };
-        auto publish = [&](long long n) {
-            const int s = (int)(n % NST);
-            mbar_arrive_on_copies(&bars[s]);
-            mbar_arrive(&bars[s]);
-        };
-        for (long long item = blockIdx.x; item < P.work_items; item += gridDim.x) {
-            long long lo = 0, hi = 0;
-            if (lane == 0) {
-                lo = item * P.item_len;
-                hi = (item + 1) * P.item_len;
-                if (hi > P.nnz || item == P.work_items - 1) hi = P.nnz;
-                if (P.offs) {
-                    if (item > 0) lo = snap_to_segment(P.offs, P.n_mu, lo, P.item_len / 2);
-                    if (hi < P.nnz) hi = snap_to_segment(P.offs, P.n_mu, hi, P.item_len / 2);
-                }
-            }
-            const long long item_lo = __shfl_sync(0xffffffffu, lo, 0), item_hi = __shfl_sync(0xffffffffu, hi, 0);
-            const long long n_tiles = (item_hi - item_lo + TN - 1) / TN;
-            // my tiles of this item: stream indices n == pw (mod NP)
-            long long ti = (pw - n_base % np + np) % np;
-            constexpr long long kStep = (long long)np * TN;
-            // (key, id) words of my current tile and of my next two sit in registers; the record of a
-            // nonzero is requested into L2 when its word has arrived, two of my tiles before it is read
-            unsigned long long w0[kU], w1[kU], w2[kU];
-#pragma unroll
-            for (int u = 0; u < kU; u++) {
-                const long long pos = item_lo + ti * TN + u * 32 + lane;
-                w0[u] = (P.keyid && pos < item_hi) ? P.keyid[pos] : 0ull;
-                w1[u] = (P.keyid && pos + kStep < item_hi) ? P.keyid[pos + kStep] : 0ull;
-                w2[u] = (P.keyid && pos + 2 * kStep < item_hi) ? P.keyid[pos + 2 * kStep] : 0ull;
-                if (P.recs && pos + kStep < item_hi)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.recs + (w1[u] & 0xffffffffull) * P.rec_words));
-            }
-            for (; ti < n_tiles; ti += np) {
-                const long long t_lo = item_lo + ti * TN;
-                const int n_rows = (int)((t_lo + TN < item_hi) ? TN : item_hi - t_lo);
-                // the tile's values, keys and flat indices are formed in registers first (the record reads
-                // are the latency-bound part), so a producer that is ahead of the ring does not idle
-                double t_val[kU];
-                int t_key[kU];
-                unsigned long long t_fa[kU], t_fb[kU], t_fx[kU];
-#pragma unroll
-                for (int u = 0; u < kU; u++) {
-                    const int i = u * 32 + lane;
-                    const bool in = i < n_rows;
-                    long long id = t_lo + i;
-                    int key = in ? 0 : -1;
-                    if (in && P.keyid) {
-                        id = (long long)(w0[u] & 0xffffffffull);
-                        key = (int)(w0[u] >> 32);
-                    }
-                    const unsigned* rec = P.recs ? P.recs + id * P.rec_words : nullptr;
-                    t_key[u] = key;
-                    if (P.fold_static) {
-                        // the whole 32-byte record in two vector loads; flat indices as fixed dot products with
-                        // per-mode strides (0 for modes a source does not use)
-                        unsigned w[8];
-                        if (in) {
-                            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rec));
-                            const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rec) + 1);
-                            w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w;
-                            w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
-                        } else {
-#pragma unroll
-                            for (int m = 0; m < 8; m++) w[m] = 0u;
-                        }
-                        t_val[u] = __hiloint2double((int)w[1], (int)w[0]);
-                        unsigned long long fa = 0, fb = 0, fx = 0;
-#pragma unroll
-                        for (int m = 0; m < 6; m++) {
-                            fa += (unsigned long long)w[2 + m] * (unsigned long long)P.smul[0][m];
-                            fb += (unsigned long long)w[2 + m] * (unsigned long long)P.smul[1][m];
-                            if (HAS_X) fx += (unsigned long long)w[2 + m] * (unsigned long long)P.smul[2][m];
-                        }
-                        t_fa[u] = in ? (P.A.kind == SRC_ROWS ? (unsigned long long)id : fa) : 0ull;
-                        t_fb[u] = in ? (P.B.kind == SRC_ROWS ? (unsigned long long)id : fb) : 0ull;
-                        t_fx[u] = (in && HAS_X) ? (P.X.kind == SRC_ROWS ? (unsigned long long)id : fx) : 0ull;
-                    } else {
-                        t_val[u] = in ? (rec ? *reinterpret_cast<const double*>(rec) : P.val[id]) : 0.0;
-                        t_fa[u] = (in && P.A.kind != SRC_NONE) ? fold_flat(P.A, rec, id) : 0ull;
-                        t_fb[u] = (in && P.B.kind != SRC_NONE) ? fold_flat(P.B, rec, id) : 0ull;
-                        t_fx[u] = (in && HAS_X) ? fold_flat(P.X, rec, id) : 0ull;
-                    }
-                    if (P.recs && t_lo + 2 * kStep + i < item_hi)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.recs + (w2[u] & 0xffffffffull) * P.rec_words));
-                    w0[u] = w1[u];
-                    w1[u] = w2[u];
-                    const long long pos3 = t_lo + 3 * kStep + i;
-                    w2[u] = (P.keyid && pos3 < item_hi) ? P.keyid[pos3] : 0ull;
-                }
-                const StageView<TN> S = acquire(n_base + ti);
-#pragma unroll
-                for (int u = 0; u < kU; u++) {
-                    const int i = u * 32 + lane;
-                    S.key()[i] = t_key[u];
-                    S.val()[i] = t_val[u];
-                    S.flat(0)[i] = t_fa[u];
-                    S.flat(1)[i] = t_fb[u];
-                    if (HAS_X) S.flat(2)[i] = t_fx[u];
-                }
-                __syncwarp();
-                // ---- asynchronous row gathers: 16-byte chunks when rows are contiguous and aligned,
-                // single doubles (any strides) otherwise; four independent copies per lane and round
-                if (!(P.debug & 4)) {
-#pragma unroll 1
-                    for (int k = 0; k < NS; k++) {
-                        if (P.bufs[k] != 2) continue;
-                        const Source& G = k == 0 ? P.A : (k == 1 ? P.B : P.X);
-                        const int units = P.units[k], pitch = P.pitch[k];
-                        const unsigned long long* fl = S.flat(k);
-                        double* dst_rows = S.rows(P.soff[k]);
-                        const int width = P.vec[k] ? 2 : 1;
-                        const long long cstride = P.vec[k] ? 2 : G.col_stride;
-                        {
-                            int row[4], col[4];
-#pragma unroll
-                            for (int c = 0; c < 4; c++) {
-                                const int e = lane + 32 * c;
-                                row[c] = e / units;
-                                col[c] = e - row[c] * units;
-                            }
-                            const int dq = 128 / units, dr = 128 - dq * units;
-                            const int total = n_rows * units;
-                            for (int b = 0; b < total; b += 128) {
-                                const double* src[4];
-                                unsigned dst[4];
-#pragma unroll
-                                for (int c = 0; c < 4; c++) {
-                                    const int rr = row[c] < n_rows ? row[c] : 0;
-                                    src[c] = G.base + (long long)fl[rr] * G.row_stride + (long long)col[c] * cstride;
-                                    dst[c] = smem_addr(dst_rows + rr * pitch + width * col[c]);
-                                }
-#pragma unroll
-                                for (int c = 0; c < 4; c++) {
-                                    if (row[c] < n_rows) {
-                                        if (P.vec[k]) cp_async16(dst[c], src[c]); else cp_async8(dst[c], src[c]);
-                                    }
-                                    col[c] += dr;
-                                    row[c] += dq;
-                                    if (col[c] >= units) { col[c] -= units; row[c]++; }
-                                }
-                            }
-                        }
-                        // rows past a partial tile are multiplied by v = 0: they must be finite
-                        if (n_rows < TN)
-                            for (int e = n_rows * pitch + lane; e < TN * pitch; e += 32) dst_rows[e] = 0.0;
-                    }
-                }
-                if (lane == 0) S.hdr()[0] = n_rows;
-                publish(n_base + ti);
-            }
-            n_base += n_tiles;
-        }
-        if (n_base % np == pw) {  // end of stream
-            const StageView<TN> S = acquire(n_base);
-            if (lane == 0) S.hdr()[0] = 0;
-            publish(n_base);
-        }
-        cp_async_wait_all();
-        return;
-    }
-
-    // =============================================================== consumers
-    const int g = lane >> 2, q = lane & 3;
-    unsigned lt;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
-    unsigned short* wq = s_queue + warp * P.queue_cap;
-    const bool omega_role = HAS_X && warp >= kConsumerWarps / 2;
-    // rows of a tile owned by this warp (shared by the Psi / Omega pair with HAS_X) and the lanes that generate them
-    constexpr int RG = HAS_X ? TN / (kConsumerWarps / 2) : TN / kConsumerWarps;
-    constexpr int GL = HAS_X ? 64 : 32;
-    const int grp = HAS_X ? (warp & (kConsumerWarps / 2 - 1)) : warp;
-    const int row0 = grp * RG;
-    const int gl = HAS_X ? lane + 32 * (warp >> 2) : lane;
-    const int kR = omega_role ? 2 : 1;  // the right operand of this warp's product: X or B
-    const int PA = P.pitch[0], PR = P.pitch[kR];
-    const bool noneA = P.bufs[0] == 0, noneR = P.bufs[kR] == 0;
-    bool pair_sync = false;  // generated tiles are shared by the pair
-#pragma unroll
-    for (int k = 0; k < NS; k++) pair_sync |= HAS_X && P.bufs[k] == 1;
-
-    double acc[MI][NJ][2];
-#pragma unroll
-    for (int i = 0; i < MI; i++)
-#pragma unroll
-        for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    auto flush = [&](double* dst_base, long long row_pitch, int ncols) {
-#pragma unroll
-        for (int i = 0; i < MI; i++)
-#pragma unroll
-            for (int j = 0; j < NJ; j++) {
-                const int row = 8 * i + g, col = 8 * j + 2 * q;
-                if (row < P.rA) {
-                    double* dst = dst_base + (long long)row * row_pitch + col;
-                    if (col < ncols && acc[i][j][0] != 0.0) atomicAdd(dst, acc[i][j][0]);
-                    if (col + 1 < ncols && acc[i][j][1] != 0.0) atomicAdd(dst + 1, acc[i][j][1]);
-                }
-                acc[i][j][0] = acc[i][j][1] = 0.0;
-            }
-    };
-    auto flush_psi = [&](long long key) { flush(P.psi + key * P.rB, (long long)P.n_mu * P.rB, P.rB); };
-
-    int cur_key = -1;
-    int s = 0;
-    unsigned fph = 0;
-    while (true) {
-        mbar_wait(&bars[s], fph);
-        const StageView<TN> S{stages + (size_t)s * P.stage_bytes};
-        const int n_rows = S.hdr()[0];
-        if (n_rows == 0) break;
-        if (row0 < n_rows) {
-            const int nr = (n_rows - row0 < RG) ? n_rows - row0 : RG;  // valid rows of this warp's slice
-            // ---- on-the-fly sources of MY rows.  Element e = row * r + col of the (nr x r) slice
-            // goes to lane e mod GL; a lane keeps CH independent hash / Horner chains in flight.  The
-            // central branch of ndtri runs for every lane without a branch (a diverged warp would
-            // issue it anyway); lanes whose uniform may fall in a tail keep the uniform in the tile
-            // and push the slot on the warp's private queue, which the same warp then drains densely.
-#pragma unroll 1
-            for (int k = 0; k < NS; k++) {
-                if (P.bufs[k] != 1 || (P.debug & 1)) continue;
-                const int r = P.units[k], pitch = P.pitch[k];
-                const unsigned long long* fl = S.flat(k) + row0;
-                const unsigned long long* salts = s_salt + 64 * k;
-                const int tbase = P.goff[k] + row0 * pitch;
-                const int total = nr * r;
-                // cursor of the lane's next element e = gl + n * GL: its row, column and tile offset
-                const unsigned magic = (65536u + (unsigned)r - 1u) / (unsigned)r;  // e / r == (e * magic) >> 16 for e < 1024, r <= 64
-                int row = (int)(((unsigned)gl * magic) >> 16);
-                int col = gl - row * r;
-                const int dq = (int)(((unsigned)GL * magic) >> 16), dr = GL - dq * r;
-                int off = tbase + row * pitch + col;
-                const int doff = dq * pitch + dr, wrap = pitch - r;
-                int wcount = 0;
-                // C elements per lane and step, all in flight together
-                auto step = [&](auto cc_tag) {
-                    constexpr int C = decltype(cc_tag)::value;
-                    bool valid[C], tail[C];
-                    int offs[C];
-                    double uu[C], cc[C];
-#pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        valid[c] = row < nr;  // rows past the slice read other words of the stage (never stored)
-                        const unsigned long long h = hash64(fl[row] + salts[col]);
-                        const unsigned hi = (unsigned)(h >> 32) & 0xFFFFFu;
-                        uu[c] = __dadd_rn(__hiloint2double((int)(hi | 0x3FF00000u), (int)(unsigned)h), -1.0);
-                        tail[c] = valid[c] && (hi - kCentralLo >= kCentralSpan);
-                        offs[c] = off;
-                        col += dr; row += dq; off += doff;
-                        if (col >= r) { col -= r; row++; off += wrap; }
-                    }
-#pragma unroll
-                    for (int c = 0; c < C; c++) cc[c] = ndtri_central(uu[c]);
-#pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        if (valid[c]) gtiles[offs[c]] = tail[c] ? uu[c] : cc[c];
-                        const unsigned m = __ballot_sync(0xffffffffu, tail[c]);
-                        if (tail[c]) wq[wcount + __popc(m & lt)] = (unsigned short)offs[c];
-                        wcount += __popc(m);
-                    }
-                };
-                const int per_lane = (total + GL - 1) / GL;  // warp-uniform
-                int n = 0;
-                for (; n + CH <= per_lane; n += CH) step(std::integral_constant<int, CH>{});
-                for (; n < per_lane; n++) step(std::integral_constant<int, 1>{});
-                // the warp's deferred tails, dense over the queue.  The generator pre-filters on the high
-                // word of the uniform only, so a (rare) entry may belong to the central branch after all.
-                __syncwarp();
-                for (int qi = lane; qi < wcount; qi += 32) {
-                    const int o = wq[qi];
-                    const double u = gtiles[o];
-                    const int cls = ndtri_class(u);
-                    gtiles[o] = (cls == 0) ? ndtri_central(u) : ndtri_tail(u, cls, s_tab);
-                }
-                // rows past a partial tile are multiplied by v = 0: they must be finite
-                if (nr < RG)
-                    for (int e = nr * pitch + gl; e < RG * pitch; e += GL) gtiles[tbase + e] = 0.0;
-            }
-            if (pair_sync) named_barrier(1 + grp, 64); else __syncwarp();
-            // ---- accumulate: k-chunks of 4 rows; the A fragment is scaled by the value
-            if (!(P.debug & 2)) {
-                const double* At = (P.bufs[0] == 2) ? S.rows(P.soff[0]) : gtiles + P.goff[0];
-                const double* Rt = (P.bufs[kR] == 2) ? S.rows(P.soff[kR]) : gtiles + P.goff[kR];
-                const double* s_val = S.val();
-                const int* s_key = S.key();
-#pragma unroll 2
-                for (int ch = 0; ch < RG / 4; ch++) {
-                    const int rbase = row0 + 4 * ch;
-                    if (rbase >= n_rows) break;  // warp-uniform
-                    const int p = rbase + q;
-                    const double v = s_val[p];  // 0 past the tile
-                    double a[MI], b[NJ];
-                    if (noneA) {  // Psi_0: the left factor is the scalar 1
-#pragma unroll
-                        for (int i = 0; i < MI; i++) a[i] = (i == 0 && g == 0) ? v : 0.0;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < MI; i++) a[i] = At[p * PA + 8 * i + g] * v;
-                    }
-                    if (noneR) {  // Psi_{d-1}: the right factor is the scalar 1
-#pragma unroll
-                        for (int j = 0; j < NJ; j++) b[j] = (j == 0 && g == 0) ? 1.0 : 0.0;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < NJ; j++) b[j] = Rt[p * PR + 8 * j + g];
-                    }
-                    bool plain = omega_role;
-                    int key = 0;
-                    if (!omega_role) {
-                        key = s_key[p];  // -1 past the tile
-                        plain = __all_sync(0xffffffffu, key == cur_key);
-                    }
-                    if (plain) {
-#pragma unroll
-                        for (int i = 0; i < MI; i++)
-#pragma unroll
-                            for (int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                    } else {
-                        // the chunk starts a new segment or straddles segment boundaries: one MMA round per run of equal keys
-                        int start = 0;
-                        while (start < 4) {
-                            const int kcur = __shfl_sync(0xffffffffu, key, start);  // lane `start` holds row rbase + start
-                            if (kcur < 0) break;
-                            if (kcur != cur_key) {
-                                if (cur_key >= 0) flush_psi(cur_key);
-                                cur_key = kcur;
-                            }
-                            const bool mine = (q >= start) && (key == kcur);
-                            const unsigned diff = __ballot_sync(0xffffffffu, (q > start) && (key != kcur)) & 0xFu;
-#pragma unroll
-                            for (int i = 0; i < MI; i++) {
-                                const double am = mine ? a[i] : 0.0;
-#pragma unroll
-                                for (int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], am, b[j]);
-                            }
-                            start = diff ? (__ffs(diff) - 1) : 4;
-                        }
-                    }
-                }
-            }
-            if (pair_sync) named_barrier(1 + grp, 64);  // the pair's generated rows may be overwritten
-        }
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();  // this warp's reads of the stage are done before the producer may overwrite it
-            atomicAdd(reinterpret_cast<unsigned*>(bars + kMaxStages) + s, 1u);
-        }
-        if (++s == NST) { s = 0; fph ^= 1u; }
-    }
-    if (omega_role) flush(P.omega, P.rX, P.rX);
-    else if (cur_key >= 0) flush_psi(cur_key);
 }
 
 // ------------------------------------------------------------------ TT-DRM chain step, bucketed
@@ -908,575 +331,9 @@ static int launch_chain(ttsk_ctx* ctx, ChainParams& C, cudaStream_t st) {
     }
 }
 
-// ------------------------------------------------------------------ the mode pass, segment-GEMM form
-// When the right sources of a pass are small prefix tables -- B = R_mu has S rows (S = product of the
-// trailing mode sizes) and X = R_{mu-1} has n_mu * S rows, the block of key j being rows
-// [j S, (j+1) S) -- the per-nonzero outer products factor through the table row index s_p:
-//     Psi_mu[:, j, :]  = T_j^T  B,          Omega_{mu-1} = sum_j T_j^T X[j S : (j+1) S],
-//     T_j[s, :]        = sum over nonzeros p of segment j with s_p = s of  v_p L_{mu-1}(p).
-// So a nonzero costs its generated left row and rA shared-memory adds instead of two gathered
-// table rows (2 * rB * 8 bytes through L2) and (rA x (rB + rX)) MMA work; the two small GEMMs run
-// once per segment (per CTA that holds a part of it).  C4's mode 2 (S = 500): 640 B of L2 gathers
-// and 7.5 DMMAs per nonzero become 20 adds.
-//
-// Warp-specialised like sparse_pass_kernel: one producer warp stages tiles of kSgTN sorted
-// positions (values, keys, flat index of the generated source, table row index) into an mbarrier
-// ring; sixteen consumer warps each generate the on-the-fly Gaussian entries of their own 16 rows,
-// drain their tail queues and add v_p * row into T (FP64 shared-memory atomics: T is shared by the
-// CTA).  All consumers see the same tile sequence, so they agree without communication on the
-// current segment; only at a segment boundary do they meet (named barrier), multiply T with the
-// tables (FP64 MMAs, K = S split over the warps), add the products to Psi / Omega and clear T.
-constexpr int kSgConsumers = 16;
-constexpr int kSgTN = 256;
-constexpr int kSgThreads = 32 * (kSgConsumers + 1);
-constexpr int kSgStages = 3;
-
-// FLAT: the last mode (no right factor): T[i_mu(p), :] += v_p L_{d-2}(p) over the nonzeros in their ORIGINAL order
-// (no bucketing at all), Psi_{d-1}[:, s, 0] = T[s, :] at the end.
-template <int MI, int NJ, bool HAS_X, bool FLAT>
-__global__ void __launch_bounds__(kSgThreads, 1) sparse_sg_kernel(const PassParams P) {
-    constexpr int TN = kSgTN;
-    constexpr int RG = TN / kSgConsumers;  // rows of a tile owned by one consumer warp
-    constexpr int CH = 2;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* s_tab = reinterpret_cast<double2*>(smem_raw);  // log table + tail coefficients
-    unsigned long long* s_salt = reinterpret_cast<unsigned long long*>(s_tab + kGaussTabEntries);  // [64]
-    unsigned long long* bars = s_salt + 64;  // full mbarriers [kSgStages], then the stages' release counters
-    unsigned char* stages = reinterpret_cast<unsigned char*>(bars + 2 * kMaxStages);
-    const int PT = P.pitch[0];
-    const int S_rows = P.sg_S, S_pad = (S_rows + 3) & ~3;
-    double* gtile = reinterpret_cast<double*>(stages + (size_t)kSgStages * P.stage_bytes);  // [TN][PT] generated rows
-    double* T = gtile + TN * PT;                                                             // [S_pad][PT]
-    unsigned short* s_queue = reinterpret_cast<unsigned short*>(T + S_pad * PT);             // [kSgConsumers][queue_cap]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    load_logtab(s_tab);
-    for (int i = tid; i < TN * PT + S_pad * PT; i += kSgThreads) gtile[i] = 0.0;
-    for (int i = tid; i < kSgStages * P.stage_bytes / 8; i += kSgThreads) reinterpret_cast<double*>(stages)[i] = 0.0;
-    if (tid < P.A.r) s_salt[tid] = hash64((unsigned long long)(P.A.rank_min + tid)) + P.A.seed;
-    if (tid == 0) {
-        for (int s = 0; s < kSgStages; s++) {
-            mbar_init(&bars[s], 32);  // one plain arrive per producer lane
-            reinterpret_cast<unsigned*>(bars + kMaxStages)[s] = 0u;
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();  // the only CTA-wide barrier
-
-    if (warp == kSgConsumers) {
-        // =========================================================== producer
-        constexpr int kU = TN / 32;
-        volatile unsigned* released = reinterpret_cast<volatile unsigned*>(bars + kMaxStages);
-        long long n = 0;  // index in the CTA's tile stream
-        auto acquire = [&]() -> StageView<TN> {
-            const int s = (int)(n % kSgStages);
-            const unsigned need = (unsigned)(n / kSgStages) * kSgConsumers;
-            wait_released(released + s, need, 2048u);
-            return StageView<TN>{stages + (size_t)s * P.stage_bytes};
-        };
-        for (long long item = blockIdx.x; item < P.work_items; item += gridDim.x) {
-            long long lo = 0, hi = 0;
-            if (lane == 0) {
-                lo = item * P.item_len;
-                hi = (item + 1) * P.item_len;
-                if (hi > P.nnz || item == P.work_items - 1) hi = P.nnz;
-                if (!FLAT) {
-                    if (item > 0) lo = snap_to_segment(P.offs, P.n_mu, lo, P.item_len / 2);
-                    if (hi < P.nnz) hi = snap_to_segment(P.offs, P.n_mu, hi, P.item_len / 2);
-                }
-            }
-            const long long item_lo = __shfl_sync(0xffffffffu, lo, 0), item_hi = __shfl_sync(0xffffffffu, hi, 0);
-            unsigned long long w0[kU], w1[kU];  // FLAT: identity order, the word is just the position
-#pragma unroll
-            for (int u = 0; u < kU; u++) {
-                const long long pos = item_lo + u * 32 + lane;
-                w0[u] = FLAT ? (unsigned long long)pos : (pos < item_hi ? P.keyid[pos] : 0ull);
-                w1[u] = FLAT ? (unsigned long long)(pos + TN) : (pos + TN < item_hi ? P.keyid[pos + TN] : 0ull);
-            }
-            for (long long t_lo = item_lo; t_lo < item_hi; t_lo += TN, n++) {
-                const int n_rows = (int)((t_lo + TN < item_hi) ? TN : item_hi - t_lo);
-                double t_val[kU];
-                int t_key[kU];
-                unsigned long long t_fa[kU];
-                int t_s[kU];
-#pragma unroll
-                for (int u = 0; u < kU; u++) {
-                    const int i = u * 32 + lane;
-                    const bool in = i < n_rows;
-                    const long long id = (long long)(w0[u] & 0xffffffffull);
-                    unsigned w[8];
-                    if (in) {
-                        const unsigned* rec = P.recs + id * 8;
-                        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rec));
-                        const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rec) + 1);
-                        w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w;
-                        w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
-                    } else {
-#pragma unroll
-                        for (int m = 0; m < 8; m++) w[m] = 0u;
-                    }
-                    unsigned long long fa = 0, fb = 0;
-#pragma unroll
-                    for (int m = 0; m < 6; m++) {
-                        fa += (unsigned long long)w[2 + m] * (unsigned long long)P.smul[0][m];
-                        fb += (unsigned long long)w[2 + m] * (unsigned long long)P.smul[1][m];
-                    }
-                    t_val[u] = __hiloint2double((int)w[1], (int)w[0]);  // 0 past the tile
-                    t_key[u] = in ? (FLAT ? 0 : (int)(w0[u] >> 32)) : -1;
-                    t_fa[u] = fa;
-                    t_s[u] = FLAT ? (int)w[2 + P.sg_mode] : (int)fb;
-                    // records of the tile after next -> L2
-                    if (t_lo + 2 * TN + i < item_hi) {
-                        const unsigned long long wn = FLAT ? (unsigned long long)(t_lo + 2 * TN + i) : P.keyid[t_lo + 2 * TN + i];
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.recs + (wn & 0xffffffffull) * 8));
-                        w0[u] = w1[u];
-                        w1[u] = wn;
-                    } else {
-                        w0[u] = w1[u];
-                        w1[u] = 0ull;
-                    }
-                }
-                const StageView<TN> S = acquire();
-#pragma unroll
-                for (int u = 0; u < kU; u++) {
-                    const int i = u * 32 + lane;
-                    S.key()[i] = t_key[u];
-                    S.val()[i] = t_val[u];
-                    S.flat(0)[i] = t_fa[u];
-                    reinterpret_cast<int*>(S.flat(1))[i] = t_s[u];
-                }
-                if (lane == 0) {
-                    S.hdr()[0] = n_rows;
-                    S.hdr()[1] = FLAT ? 0 : (int)(P.keyid[t_lo] >> 32);
-                    S.hdr()[2] = FLAT ? 0 : (int)(P.keyid[t_lo + n_rows - 1] >> 32);
-                }
-                mbar_arrive(&bars[n % kSgStages]);
-            }
-        }
-        {   // end of stream
-            const StageView<TN> S = acquire();
-            if (lane == 0) S.hdr()[0] = 0;
-            mbar_arrive(&bars[n % kSgStages]);
-        }
-        return;
-    }
-
-    // =============================================================== consumers
-    const int g = lane >> 2, q = lane & 3;
-    unsigned lt;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
-    unsigned short* wq = s_queue + warp * P.queue_cap;
-    const int row0 = warp * RG;
-    const int rA = P.A.r;
-    const unsigned magic = (65536u + (unsigned)rA - 1u) / (unsigned)rA;  // e / rA == (e * magic) >> 16 for e < 1024
-    const int dq = (int)((32u * magic) >> 16), dr = 32 - dq * rA;
-    const int crow = (int)(((unsigned)lane * magic) >> 16), ccol = lane - crow * rA;  // cursor of element e = lane
-
-    // Psi[:, key, :] += T^T Btab   and   Omega += T^T Xtab[key S : (key+1) S]; then T = 0.  All consumers.
-    auto segment_gemm = [&](int key) {
-        named_barrier(1, 32 * kSgConsumers);  // every warp has finished adding to T
-        const bool omega_role = HAS_X && warp >= kSgConsumers / 2;
-        const int role_warps = HAS_X ? kSgConsumers / 2 : kSgConsumers;
-        const int role_rank = HAS_X ? (warp & (kSgConsumers / 2 - 1)) : warp;
-        const Source& R = omega_role ? P.X : P.B;
-        const int rR = omega_role ? P.rX : P.rB;
-        const double* tab = R.base + (omega_role ? (long long)key * S_rows * R.row_stride : 0ll);
-        double acc[MI][NJ][2];
-#pragma unroll
-        for (int i = 0; i < MI; i++)
-#pragma unroll
-            for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-        for (int ch = role_rank; 4 * ch < S_pad; ch += role_warps) {
-            const int srow = 4 * ch + q;
-            double a[MI], b[NJ];
-#pragma unroll
-            for (int i = 0; i < MI; i++) a[i] = T[srow * PT + 8 * i + g];
-            const double* brow = tab + (long long)srow * R.row_stride;
-#pragma unroll
-            for (int j = 0; j < NJ; j++) b[j] = (srow < S_rows && 8 * j + g < rR) ? __ldg(brow + 8 * j + g) : 0.0;
-#pragma unroll
-            for (int i = 0; i < MI; i++)
-#pragma unroll
-                for (int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
-        double* dst_base = omega_role ? P.omega : P.psi + (long long)key * P.rB;
-        const long long row_pitch = omega_role ? (long long)P.rX : (long long)P.n_mu * P.rB;
-#pragma unroll
-        for (int i = 0; i < MI; i++)
-#pragma unroll
-            for (int j = 0; j < NJ; j++) {
-                const int row = 8 * i + g, col = 8 * j + 2 * q;
-                if (row < rA) {
-                    double* dst = dst_base + (long long)row * row_pitch + col;
-                    if (col < rR && acc[i][j][0] != 0.0) atomicAdd(dst, acc[i][j][0]);
-                    if (col + 1 < rR && acc[i][j][1] != 0.0) atomicAdd(dst + 1, acc[i][j][1]);
-                }
-            }
-        named_barrier(1, 32 * kSgConsumers);  // all products read T
-        for (int i = tid; i < S_pad * PT; i += 32 * kSgConsumers) T[i] = 0.0;
-        named_barrier(1, 32 * kSgConsumers);
-    };
-
-    int t_key = FLAT ? 0 : -1;  // the segment T belongs to
-    int s = 0;
-    unsigned fph = 0;
-    while (true) {
-        mbar_wait(&bars[s], fph);
-        const StageView<TN> S{stages + (size_t)s * P.stage_bytes};
-        const int n_rows = S.hdr()[0];
-        if (n_rows == 0) break;
-        const int key_first = S.hdr()[1], key_last = S.hdr()[2];
-        const int nr = (n_rows - row0 < RG) ? n_rows - row0 : RG;  // valid rows of this warp's slice (may be <= 0)
-        const double* s_val = S.val() + row0;
-        const int* s_idx = reinterpret_cast<const int*>(S.flat(1)) + row0;
-        double* mine = gtile + row0 * PT;
-        // ---- generated rows of my slice (see sparse_pass_kernel)
-        if (nr > 0 && !(P.debug & 1)) {
-            const unsigned long long* fl = S.flat(0) + row0;
-            int row = crow, col = ccol, off = crow * PT + ccol;
-            const int doff = dq * PT + dr, wrap = PT - rA;
-            int wcount = 0;
-            auto step = [&](auto cc_tag) {
-                constexpr int C = decltype(cc_tag)::value;
-                bool valid[C], tail[C];
-                int offs[C];
-                double uu[C], cc[C];
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    valid[c] = row < nr;
-                    const unsigned long long h = hash64(fl[row] + s_salt[col]);
-                    const unsigned hi = (unsigned)(h >> 32) & 0xFFFFFu;
-                    uu[c] = __dadd_rn(__hiloint2double((int)(hi | 0x3FF00000u), (int)(unsigned)h), -1.0);
-                    tail[c] = valid[c] && (hi - kCentralLo >= kCentralSpan);
-                    offs[c] = off;
-                    col += dr; row += dq; off += doff;
-                    if (col >= rA) { col -= rA; row++; off += wrap; }
-                }
-#pragma unroll
-                for (int c = 0; c < C; c++) cc[c] = ndtri_central(uu[c]);
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    if (valid[c]) mine[offs[c]] = tail[c] ? uu[c] : cc[c];
-                    const unsigned m = __ballot_sync(0xffffffffu, tail[c]);
-                    if (tail[c]) wq[wcount + __popc(m & lt)] = (unsigned short)offs[c];
-                    wcount += __popc(m);
-                }
-            };
-            const int per_lane = (nr * rA + 31) / 32;  // warp-uniform
-            int k = 0;
-            for (; k + CH <= per_lane; k += CH) step(std::integral_constant<int, CH>{});
-            for (; k < per_lane; k++) step(std::integral_constant<int, 1>{});
-            __syncwarp();
-            for (int qi = lane; qi < wcount; qi += 32) {
-                const int o = wq[qi];
-                const double u = mine[o];
-                const int cls = ndtri_class(u);
-                mine[o] = (cls == 0) ? ndtri_central(u) : ndtri_tail(u, cls, s_tab);
-            }
-            __syncwarp();
-        }
-        // ---- T[s_p, :] += v_p * row_p for my rows in [ra, rb) (slice-relative)
-        auto accumulate = [&](int ra, int rb) {
-            if (P.debug & 2) return;
-            const int n_el = (rb - ra) * rA;
-            int row = ra + crow, col = ccol;
-            for (int e = lane; e < n_el; e += 32) {
-                const double x = mine[row * PT + col] * s_val[row];
-                atomicAdd(&T[s_idx[row] * PT + col], x);
-                col += dr; row += dq;
-                if (col >= rA) { col -= rA; row++; }
-            }
-        };
-        if (key_first == t_key && key_last == t_key) {
-            if (nr > 0) accumulate(0, nr);
-        } else {
-            // the tile starts a new segment or holds several: walk its runs of equal keys (every
-            // consumer warp takes the same decisions, so the barriers inside segment_gemm match up)
-            const int* keys = S.key();
-            int pos = 0;
-            while (pos < n_rows) {
-                const int k = keys[pos];
-                int lo = pos, hi = n_rows;  // first index in (pos, n_rows] whose key differs
-                while (lo + 1 < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (keys[mid] == k) lo = mid; else hi = mid;
-                }
-                const int end = lo + 1;
-                if (k != t_key) {
-                    if (t_key >= 0) segment_gemm(t_key);
-                    t_key = k;
-                }
-                const int ra = (pos > row0 ? pos : row0) - row0, rb = (end < row0 + RG ? end : row0 + RG) - row0;
-                if (rb > ra) accumulate(ra, rb);
-                pos = end;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            atomicAdd(reinterpret_cast<unsigned*>(bars + kMaxStages) + s, 1u);
-        }
-        if (++s == kSgStages) { s = 0; fph ^= 1u; }
-    }
-    if (FLAT) {
-        named_barrier(1, 32 * kSgConsumers);  // every warp has finished adding to T
-        for (int e = tid; e < S_rows * rA; e += 32 * kSgConsumers) {
-            const int srow = e / rA, a = e - srow * rA;
-            const double x = T[srow * PT + a];
-            if (x != 0.0) atomicAdd(P.psi + (long long)a * P.n_mu + srow, x);  // Psi_{d-1} is (rA, n_mu, 1)
-        }
-    } else if (t_key >= 0) {
-        segment_gemm(t_key);
-    }
-}
-
-// last mode without bucketing (see FLAT above): taken when the mode is small enough for T to sit in shared memory
-template <int MI>
-static int try_launch_sg_flat(ttsk_ctx* ctx, PassParams& P, cudaStream_t st, bool* used) {
-    *used = false;
-    static const int disabled = getenv("TTSK_NO_SG") ? atoi(getenv("TTSK_NO_SG")) : 0;
-    if (disabled || !P.recs || P.rec_words != 8) return TTSK_OK;
-    if (P.A.kind != SRC_GAUSS || P.B.kind != SRC_NONE || P.n_mu > 1024 || P.sg_mode < 0 || P.sg_mode >= 6) return TTSK_OK;
-    if (P.nnz < 65536) return TTSK_OK;
-    for (int m = 0; m < 6; m++) P.smul[0][m] = P.smul[1][m] = P.smul[2][m] = 0;
-    for (int i = 0; i < P.A.k; i++) {
-        if (P.A.modes[i] >= 6) return TTSK_OK;
-        P.smul[0][P.A.modes[i]] += P.A.strides[i];
-    }
-    P.fold_static = 1;
-    P.sg_S = (int)P.n_mu;
-    P.pitch[0] = tile_pitch(MI);
-    P.stage_bytes = stage_header_bytes(kSgTN);
-    const int S_pad = ((int)P.n_mu + 3) & ~3;
-    P.queue_cap = (32 * ((kSgTN / kSgConsumers * P.A.r + 31) / 32 + 2) + 7) & ~7;
-    const size_t smem = (size_t)kGaussTabEntries * 16 + 64 * 8 + 2 * kMaxStages * 8 + (size_t)kSgStages * P.stage_bytes +
-                        ((size_t)kSgTN + S_pad) * P.pitch[0] * 8 + (size_t)kSgConsumers * P.queue_cap * 2 + 64;
-    if (smem > 227 * 1024) return TTSK_OK;
-    auto kern = sparse_sg_kernel<MI, 1, false, true>;
-    TTSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long grid = ctx->sm_count;
-    long long items = grid * 8;
-    const long long min_len = 8192;
-    if (items * min_len > P.nnz) items = (P.nnz + min_len - 1) / min_len;
-    if (items < 1) items = 1;
-    P.work_items = items;
-    P.item_len = (P.nnz + items - 1) / items;
-    P.debug = getenv("TTSK_ABLATE") ? atoi(getenv("TTSK_ABLATE")) : 0;
-    if (grid > items) grid = items;
-    if (getenv("TTSK_DEBUG"))
-        fprintf(stderr, "[ttsk] unbucketed last-mode pass MI=%d n_mu=%lld smem=%zu grid=%lld items=%lld\n", MI, P.n_mu, smem, grid, items);
-    kern<<<(unsigned)grid, kSgThreads, smem, st>>>(P);
-    TTSK_LAUNCHED(ctx);
-    ctx->sg_passes++;
-    *used = true;
-    return TTSK_OK;
-}
-
-// conditions and launch of the segment-GEMM form; returns TTSK_OK and sets *used when it ran
-template <int MI, int NJ, bool HAS_X>
-static int try_launch_sg(ttsk_ctx* ctx, PassParams& P, cudaStream_t st, bool* used) {
-    *used = false;
-    static const int disabled = getenv("TTSK_NO_SG") ? atoi(getenv("TTSK_NO_SG")) : 0;
-    if (disabled || !P.recs || P.rec_words != 8 || !P.keyid || !P.offs) return TTSK_OK;
-    if (P.A.kind != SRC_GAUSS || P.B.kind != SRC_TABLE || P.B.col_stride != 1) return TTSK_OK;
-    if (HAS_X && (P.X.kind != SRC_TABLE || P.X.col_stride != 1)) return TTSK_OK;
-    const long long S_rows = P.B.span_bytes / (8 * (long long)P.B.r);
-    if (S_rows < 1 || S_rows > 1024 || P.nnz < 512 * P.n_mu) return TTSK_OK;  // long segments only
-    // per-mode strides: B must not depend on the pass mode; X = B's index + key * S
-    long long smul[3][6];
-    const Source* src[3] = {&P.A, &P.B, &P.X};
-    for (int k = 0; k < 3; k++) {
-        for (int m = 0; m < 6; m++) smul[k][m] = 0;
-        if (k == 2 && !HAS_X) continue;
-        for (int i = 0; i < src[k]->k; i++) {
-            if (src[k]->modes[i] >= 6) return TTSK_OK;
-            smul[k][src[k]->modes[i]] += src[k]->strides[i];
-        }
-    }
-    if (P.sg_mode < 0 || P.sg_mode >= 6 || smul[1][P.sg_mode] != 0) return TTSK_OK;
-    if (HAS_X) {
-        for (int m = 0; m < 6; m++)
-            if (smul[2][m] != (m == P.sg_mode ? S_rows : smul[1][m])) return TTSK_OK;
-        if (P.X.span_bytes != P.n_mu * S_rows * 8 * (long long)P.X.r) return TTSK_OK;
-    }
-    for (int k = 0; k < 3; k++)
-        for (int m = 0; m < 6; m++) P.smul[k][m] = smul[k][m];
-    P.fold_static = 1;
-    P.sg_S = (int)S_rows;
-    P.pitch[0] = tile_pitch(MI);
-    P.stage_bytes = stage_header_bytes(kSgTN);
-    const int S_pad = ((int)S_rows + 3) & ~3;
-    P.queue_cap = (32 * ((kSgTN / kSgConsumers * P.A.r + 31) / 32 + 2) + 7) & ~7;
-    const size_t smem = (size_t)kGaussTabEntries * 16 + 64 * 8 + 2 * kMaxStages * 8 + (size_t)kSgStages * P.stage_bytes +
-                        ((size_t)kSgTN + S_pad) * P.pitch[0] * 8 + (size_t)kSgConsumers * P.queue_cap * 2 + 64;
-    if (smem > 227 * 1024) return TTSK_OK;
-    auto kern = sparse_sg_kernel<MI, NJ, HAS_X, false>;
-    TTSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long grid = ctx->sm_count;
-    long long items = grid * 8;
-    const long long min_len = 8192;
-    if (items * min_len > P.nnz) items = (P.nnz + min_len - 1) / min_len;
-    if (items < 1) items = 1;
-    P.work_items = items;
-    P.item_len = (P.nnz + items - 1) / items;
-    P.debug = getenv("TTSK_ABLATE") ? atoi(getenv("TTSK_ABLATE")) : 0;
-    if (grid > items) grid = items;
-    if (getenv("TTSK_DEBUG"))
-        fprintf(stderr, "[ttsk] segment-GEMM pass MI=%d NJ=%d X=%d S=%lld smem=%zu grid=%lld items=%lld\n", MI, NJ, (int)HAS_X,
-                S_rows, smem, grid, items);
-    kern<<<(unsigned)grid, kSgThreads, smem, st>>>(P);
-    TTSK_LAUNCHED(ctx);
-    ctx->sg_passes++;
-    *used = true;
-    return TTSK_OK;
-}
-
-// per-source plan for a tile height `tn` with `ch` generator chains; returns the kernel's shared-memory bytes
-// (must match its carve-up) for the largest stage count that fits `budget` bytes
-template <int MI, int NJ, bool HAS_X>
-static size_t plan_pass(PassParams& P, int tn, int ch, size_t budget, int want_stages) {
-    const Source* src[3] = {&P.A, &P.B, &P.X};
-    const int pitches[3] = {tile_pitch(MI), tile_pitch(NJ), tile_pitch(NJ)};
-    int soff = stage_header_bytes(tn), goff = 0, max_elems = 1;
-    for (int k = 0; k < 3; k++) {
-        const Source& S = *src[k];
-        P.pitch[k] = pitches[k];
-        P.bufs[k] = 0; P.units[k] = 1; P.vec[k] = 0; P.soff[k] = 0; P.goff[k] = 0;
-        if ((k == 2 && !HAS_X) || S.kind == SRC_NONE) continue;
-        if (S.kind == SRC_GAUSS) {
-            P.bufs[k] = 1;
-            P.units[k] = S.r;
-            P.goff[k] = goff;
-            goff += tn * P.pitch[k];
-            max_elems = std::max(max_elems, (tn * S.r + 255) / 256 + ch);  // per lane and tile, rounded up to whole chain groups
-        } else {
-            P.bufs[k] = 2;
-            const bool aligned = S.col_stride == 1 && (S.r % 2 == 0) && (S.row_stride % 2 == 0) &&
-                                 (reinterpret_cast<uintptr_t>(S.base) % 16 == 0);
-            P.vec[k] = aligned ? 1 : 0;
-            P.units[k] = aligned ? S.r / 2 : S.r;
-            P.soff[k] = soff;
-            soff += tn * P.pitch[k] * 8;
-        }
-    }
-    P.fold_static = (P.recs != nullptr && P.rec_words == 8) ? 1 : 0;
-    for (int k = 0; k < 3; k++) {
-        for (int m = 0; m < 6; m++) P.smul[k][m] = 0;
-        const Source& S = *src[k];
-        if ((k == 2 && !HAS_X) || (S.kind != SRC_GAUSS && S.kind != SRC_TABLE)) continue;
-        for (int i = 0; i < S.k; i++) {
-            if (S.modes[i] < 6) P.smul[k][S.modes[i]] += S.strides[i];
-            else P.fold_static = 0;
-        }
-    }
-    P.stage_bytes = soff;
-    P.gen_doubles = goff;
-    P.queue_cap = (32 * max_elems + 7) & ~7;
-    const size_t fixed = (size_t)kGaussTabEntries * 16 + 192 * 8 + 2 * kMaxStages * 8 + (size_t)goff * 8 +
-                         (size_t)kConsumerWarps * P.queue_cap * 2 + 64;
-    int nst = want_stages;
-    while (nst > 2 && fixed + (size_t)nst * soff > budget) nst--;
-    P.nstages = nst;
-    return fixed + (size_t)nst * soff;
-}
-
-template <int MI, int NJ, bool HAS_X, int TN, int CH, int NP>
-static int launch_pass_t(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
-    auto kern = sparse_pass_kernel<MI, NJ, HAS_X, TN, CH, NP>;
-    constexpr int kPassThreads = pass_threads(NP);
-    auto gathered = [](const Source& S) { return S.kind == SRC_ROWS || S.kind == SRC_TABLE; };
-    const bool gathers = gathered(P.A) || gathered(P.B) || (HAS_X && gathered(P.X));
-    // generated sources only: small stages, several CTAs per SM; gathered rows: one CTA per SM with a deep ring
-    const size_t smem = plan_pass<MI, NJ, HAS_X>(P, TN, CH, !gathers ? 72 * 1024 : 226 * 1024,
-                                                 gathers ? kMaxStages : 4);
-    P.smem_bytes = (int)smem;
-    TTSK_ARG(smem <= 227 * 1024, "sparse pass: shared-memory plan exceeds 227 KB (ranks too large)");
-    TTSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TTSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int per_sm = 1;
-    TTSK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPassThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)ctx->sm_count * per_sm;
-    // ~8 work items per CTA for balance, none shorter than a few dozen tiles
-    long long items = grid * 8;
-    const long long min_len = 4096;
-    if (items * min_len > P.nnz) items = (P.nnz + min_len - 1) / min_len;
-    if (items < 1) items = 1;
-    P.work_items = items;
-    P.item_len = (P.nnz + items - 1) / items;
-    P.debug = getenv("TTSK_ABLATE") ? atoi(getenv("TTSK_ABLATE")) : 0;
-    if (grid > items) grid = items;
-    if (grid < 1) grid = 1;
-    if (getenv("TTSK_DEBUG"))
-        fprintf(stderr, "[ttsk] pass MI=%d NJ=%d X=%d TN=%d CH=%d smem=%zu stages=%d x %d B ctas/sm=%d grid=%lld items=%lld bufs=%d%d%d vec=%d%d%d\n",
-                MI, NJ, (int)HAS_X, TN, CH, smem, P.nstages, P.stage_bytes, per_sm, grid, items, P.bufs[0], P.bufs[1], P.bufs[2],
-                P.vec[0], P.vec[1], P.vec[2]);
-    kern<<<(unsigned)grid, kPassThreads, smem, st>>>(P);
-    TTSK_LAUNCHED(ctx);
-    return TTSK_OK;
-}
-
-// generated sources only: 128-row tiles, two generator chains per lane, one producer warp, several CTAs per SM;
-// with gathered rows: 64-row tiles in a deep ring, one CTA per SM, four chains per lane, four producer warps
-template <int MI, int NJ, bool HAS_X>
-static int launch_pass_tn(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
-    if constexpr (HAS_X && MI * NJ <= 15) {  // the fused path only reaches this form on middle modes (X present)
-        bool used = false;
-        TTSK_TRY((try_launch_sg<MI, NJ, HAS_X>(ctx, P, st, &used)));
-        if (used) return TTSK_OK;
-    }
-    auto gathered = [](const Source& S) { return S.kind == SRC_ROWS || S.kind == SRC_TABLE; };
-    const bool gathers = gathered(P.A) || gathered(P.B) || (HAS_X && gathered(P.X));
-    static const int forced = getenv("TTSK_TN") ? atoi(getenv("TTSK_TN")) : 0;
-    int tn = gathers ? 64 : 128;
-    if (forced == 64 || forced == 128) tn = forced;
-    if (tn == 128 && plan_pass<MI, NJ, HAS_X>(P, 128, 2, 227 * 1024, 2) > 227 * 1024) tn = 64;
-    if (tn == 128) return launch_pass_t<MI, NJ, HAS_X, 128, 2, 1>(ctx, P, st);
-    // nothing to generate: the pass is bound by how many row copies are in flight -> eight producer warps
-    auto generated = [](const Source& S) { return S.kind == SRC_GAUSS; };
-    const bool any_gen = generated(P.A) || generated(P.B) || (HAS_X && generated(P.X));
-    static const int np_env = getenv("TTSK_NP") ? atoi(getenv("TTSK_NP")) : 0;
-    if constexpr (MI * NJ <= 15) {
-        if ((!any_gen && np_env != 4) || np_env == 8) return launch_pass_t<MI, NJ, HAS_X, 64, 4, 8>(ctx, P, st);
-    }
-    return launch_pass_t<MI, NJ, HAS_X, 64, 4, 4>(ctx, P, st);
-}
-
-template <bool HAS_X>
-static int launch_pass_x(ttsk_ctx* ctx, PassParams& P, cudaStream_t st) {
-    const int mi = (P.rA + 7) / 8;
-    const int nj = (std::max(P.rB, HAS_X ? P.rX : 1) + 7) / 8;
-    TTSK_ARG(mi <= 8 && nj <= 8, "sparse pass: DRM rank above 64 is not supported by the fused kernel");
-#define TTSK_PASS(MI_, NJ_) return launch_pass_tn<MI_, NJ_, HAS_X>(ctx, P, st)
-    const int MIr = mi <= 1 ? 1 : (mi <= 3 ? 3 : (mi <= 5 ? 5 : 8));
-    const int NJr = nj <= 1 ? 1 : (nj <= 3 ? 3 : (nj <= 5 ? 5 : 8));
-    switch (MIr * 10 + NJr) {
-        case 11: TTSK_PASS(1, 1);
-        case 13: TTSK_PASS(1, 3);
-        case 15: TTSK_PASS(1, 5);
-        case 18: TTSK_PASS(1, 8);
-        case 31: TTSK_PASS(3, 1);
-        case 33: TTSK_PASS(3, 3);
-        case 35: TTSK_PASS(3, 5);
-        case 38: TTSK_PASS(3, 8);
-        case 51: TTSK_PASS(5, 1);
-        case 53: TTSK_PASS(5, 3);
-        case 55: TTSK_PASS(5, 5);
-        case 58: TTSK_PASS(5, 8);
-        case 81: TTSK_PASS(8, 1);
-        case 83: TTSK_PASS(8, 3);
-        case 85: TTSK_PASS(8, 5);
-        case 88: TTSK_PASS(8, 8);
-    }
-#undef TTSK_PASS
-    set_error("sparse pass: no kernel variant");
-    return TTSK_E_ARG;
-}
-
 static int launch_pass(ttsk_ctx* ctx, PassParams& P, bool has_x, cudaStream_t st) {
     if (P.nnz <= 0) return TTSK_OK;
-    return has_x ? launch_pass_x<true>(ctx, P, st) : launch_pass_x<false>(ctx, P, st);
+    return has_x ? launch_pass_with_x(ctx, P, st) : launch_pass_without_x(ctx, P, st);
 }
 
 // ---- sort buffers (workspace views) and the bucket pass
@@ -1742,12 +599,8 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
             return TTSK_OK;
         };
         if (mu == d - 1 && !has_x) {  // last mode: no bucketing needed when the mode fits shared memory
-            const int mi = (P.rA + 7) / 8;
             TTSK_TRY(mark(0));
-            if (mi <= 1) TTSK_TRY(try_launch_sg_flat<1>(ctx, P, st, &flat_done));
-            else if (mi <= 3) TTSK_TRY(try_launch_sg_flat<3>(ctx, P, st, &flat_done));
-            else if (mi <= 5) TTSK_TRY(try_launch_sg_flat<5>(ctx, P, st, &flat_done));
-            else if (mi <= 8) TTSK_TRY(try_launch_sg_flat<8>(ctx, P, st, &flat_done));
+            TTSK_TRY(launch_last_mode_unbucketed(ctx, P, st, &flat_done));
             if (flat_done) { TTSK_TRY(mark(1)); continue; }
         }
         TTSK_TRY(sort_keys(ctx, nnz, idx_rows[mu], shape[mu], sb, st));
