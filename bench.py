@@ -338,7 +338,10 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e_ms = float(te[0])
+        a2, b2 = c_double(), c_double()
+        be.check(lib.ttsk_last_kernel_ms(ctx, byref(a2), byref(b2)))
         e2e = {"value": nnz / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
+               "device_span_ms_last_step": a2.value, "pass_kernels_ms_last_step": b2.value,
                "h2d_bytes_per_step": int(n_loc * ALGO_BYTES_PER_NNZ), "d2h_bytes_per_step": int(total * 8),
                "api": "ttsk_sparse_sketch_host (C ABI, pinned host COO in, packed sketch out)"
                if world == 1 else "ttsk_sparse_sketch_stream + NCCL all-reduce + D2H",
