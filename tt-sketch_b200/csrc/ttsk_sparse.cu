@@ -153,8 +153,12 @@ __global__ void scatter_kernel(const ScatterParams S) {
 // Two-level scatter for n_mu <= kLocalBins: the start of every (CTA, key) range was derived from the
 // histogram kernel's per-CTA counts (deterministic bucket layout, no global atomics); a CTA only
 // ranks the nonzeros of its contiguous block within their key with shared-memory atomics.
+// The words of one (CTA, key) range are written 8 bytes at a time over the whole lifetime of the CTA; with
+// grid * n_mu open ranges the partially written sectors do not fit L2 and go to DRAM half empty.  The block is
+// therefore scattered in `rounds` sweeps over disjoint key ranges (re-reading the keys, which stream), so only
+// grid * n_mu / rounds ranges are open at a time.
 __global__ void __launch_bounds__(1024) scatter_local_kernel(const ScatterParams S, long long block_len, int n_mu,
-                                                             const int* __restrict__ cta_base) {
+                                                             const int* __restrict__ cta_base, int rounds) {
     extern __shared__ int s_bins[];
     int* s_cnt = s_bins;
     int* s_base = s_bins + n_mu;
@@ -165,10 +169,15 @@ __global__ void __launch_bounds__(1024) scatter_local_kernel(const ScatterParams
     __syncthreads();
     const long long b0 = (long long)blockIdx.x * block_len;
     const long long b1 = (b0 + block_len < S.nnz) ? b0 + block_len : S.nnz;
-    for (long long p = b0 + threadIdx.x; p < b1; p += blockDim.x) {
-        const int key = (int)S.key_idx[p];
-        const int pos = s_base[key] + atomicAdd(&s_cnt[key], 1);
-        S.keyid[pos] = ((unsigned long long)(unsigned)key << 32) | (unsigned long long)(unsigned)p;
+    const int span = (n_mu + rounds - 1) / rounds;
+    for (int r = 0; r < rounds; r++) {
+        const unsigned klo = (unsigned)(r * span);
+        for (long long p = b0 + threadIdx.x; p < b1; p += blockDim.x) {
+            const int key = (int)__ldcs(S.key_idx + p);
+            if ((unsigned)key - klo >= (unsigned)span) continue;
+            const int pos = s_base[key] + atomicAdd(&s_cnt[key], 1);
+            S.keyid[pos] = ((unsigned long long)(unsigned)key << 32) | (unsigned long long)(unsigned)p;
+        }
     }
 }
 
@@ -400,7 +409,12 @@ static int sort_keys(ttsk_ctx* ctx, int64_t nnz, const long long* key_idx, int64
         TTSK_CUDA(cudaFuncSetAttribute(scatter_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cta_base_kernel<<<(unsigned)((n_mu + 255) / 256), 256, 0, st>>>(sb.cta_cnt, sb.offs, (int)n_mu, (int)local_grid);
         TTSK_LAUNCHED(ctx);
-        scatter_local_kernel<<<(unsigned)local_grid, 1024, smem, st>>>(S, block_len, (int)n_mu, sb.cta_cnt);
+        static const int rounds_env = getenv("TTSK_SORT_ROUNDS") ? atoi(getenv("TTSK_SORT_ROUNDS")) : 0;
+        int rounds = (int)((local_grid * n_mu * 128 + ((int64_t)48 << 20) - 1) / ((int64_t)48 << 20));  // open ranges x one line each
+        if (rounds > 8) rounds = 8;
+        if (rounds_env > 0) rounds = rounds_env;
+        if (rounds < 1) rounds = 1;
+        scatter_local_kernel<<<(unsigned)local_grid, 1024, smem, st>>>(S, block_len, (int)n_mu, sb.cta_cnt, rounds);
     } else {
         scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(S);
     }
