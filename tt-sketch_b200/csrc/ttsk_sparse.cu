@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(1024) scatter_local_kernel(const ScatterParams
 // v_out[p, b] = sum_a v_in[p, a] * core[a, idx[p], b]   (first core: v_out[p, b] = core[0, idx[p], b])
 __global__ void __launch_bounds__(256) ttdrm_step_kernel(long long nnz, const long long* __restrict__ idx,
                                                         const double* __restrict__ v_in, int r_in,
+                                                        const long long* __restrict__ vin_idx, long long vin_stride,
                                                         const double* __restrict__ core, long long n, int r_out,
                                                         double* __restrict__ v_out) {
     const long long total = nnz * (long long)r_out;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(256) ttdrm_step_kernel(long long nnz, const lo
         } else {
             s = 0.0;
             const double* c = core + j * r_out + b;
-            const double* v = v_in + p * r_in;
+            const double* v = v_in + (vin_idx ? vin_idx[p] : p) * vin_stride;  // level 1 reads rows of the first core directly
             for (int a = 0; a < r_in; a++) s = fma(v[a], c[(long long)a * n * r_out], s);
         }
         v_out[e] = s;
@@ -217,7 +218,9 @@ struct ChainParams {
     const int* offs;
     long long work_items, item_len;
     const double* core;   // (r_in, n_mu, r_out)
-    const double* v_in;   // (chunk, r_in) by nonzero id
+    const double* v_in;   // row of nonzero id at v_in + (vin_idx ? vin_idx[id] : id) * vin_stride
+    const long long* vin_idx;  // level 1: index row of the level-0 mode (v_in is the first core itself)
+    long long vin_stride;
     double* v_out;        // (chunk, r_out) by nonzero id
     int r_in, r_out, pitch;
 };
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(256) ttdrm_chain_kernel(const ChainParams C) {
             if (8 * warp < len) {
                 const bool valid = row < len;
                 const long long id = valid ? (long long)(s_w[row] & 0xffffffffull) : 0;
-                const double* vin = C.v_in + id * C.r_in;
+                const double* vin = C.v_in + (C.vin_idx ? C.vin_idx[id] : id) * C.vin_stride;
                 double acc[NJ][2];
 #pragma unroll
                 for (int j = 0; j < NJ; j++) acc[j][0] = acc[j][1] = 0.0;
@@ -486,12 +489,13 @@ struct SideState {
 };
 
 static int ttdrm_step(ttsk_ctx* ctx, int64_t nnz, const long long* idx_mu, const double* v_in, int r_in,
-                      const double* core, int64_t n, int r_out, double* v_out, cudaStream_t st) {
+                      const long long* vin_idx, int64_t vin_stride, const double* core, int64_t n, int r_out,
+                      double* v_out, cudaStream_t st) {
     if (nnz <= 0) return TTSK_OK;
     const long long total = (long long)nnz * r_out;
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
-    ttdrm_step_kernel<<<(unsigned)blocks, 256, 0, st>>>(nnz, idx_mu, v_in, r_in, core, n, r_out, v_out);
+    ttdrm_step_kernel<<<(unsigned)blocks, 256, 0, st>>>(nnz, idx_mu, v_in, r_in, vin_idx, vin_stride, core, n, r_out, v_out);
     TTSK_LAUNCHED(ctx);
     return TTSK_OK;
 }
@@ -532,9 +536,9 @@ struct SparsePlan {
 static int64_t chunk_bytes_per_nnz(int d, const ttsk_drm* left, const ttsk_drm* right) {
     int64_t b = 8 + 4 * rec_words_for(d);  // sorted (key, id) words + packed records
     if (left->kind == TTSK_DRM_TT)
-        for (int k = 0; k < d - 1; k++) b += 8LL * left->core_r1[k];
+        for (int k = 1; k < d - 1; k++) b += 8LL * left->core_r1[k];
     if (right->kind == TTSK_DRM_TT)
-        for (int k = 0; k < d - 1; k++) b += 8LL * right->core_r1[k];
+        for (int k = 1; k < d - 1; k++) b += 8LL * right->core_r1[k];
     return b;
 }
 
@@ -549,20 +553,26 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
         const ttsk_drm* drm = side == 0 ? left : right;
         SideState& ss = side == 0 ? pl.left : pl.right;
         if (drm->kind != TTSK_DRM_TT) continue;
-        for (int k = 0; k < d - 1; k++) {
+        // level 0 is the first core itself (a table indexed by that mode: no buffer, see build_plan)
+        const int mode0 = side == 0 ? 0 : d - 1;
+        const long long* idx_0 = (const long long*)(d_idx + mode0 * idx_row_stride);
+        for (int k = 1; k < d - 1; k++) {
             const int mode = side == 0 ? k : d - 1 - k;
             const long long* idx_m = (const long long*)(d_idx + mode * idx_row_stride);
-            const bool bucketed = k > 0 && nnz >= 4096 && drm->core_r1[k] <= 64 && drm->core_r0[k] <= 64;
+            const double* v_in = k == 1 ? drm->d_cores[0] : ss.chain[k - 1];
+            const long long* vin_idx = k == 1 ? idx_0 : nullptr;
+            const int64_t vin_stride = k == 1 ? drm->core_r1[0] : drm->core_r0[k];
+            const bool bucketed = nnz >= 4096 && drm->core_r1[k] <= 64 && drm->core_r0[k] <= 64;
             if (!bucketed) {
-                TTSK_TRY(ttdrm_step(ctx, nnz, idx_m, k == 0 ? nullptr : ss.chain[k - 1], drm->core_r0[k],
-                                    drm->d_cores[k], shape[mode], drm->core_r1[k], ss.chain[k], st));
+                TTSK_TRY(ttdrm_step(ctx, nnz, idx_m, v_in, drm->core_r0[k], vin_idx, vin_stride, drm->d_cores[k],
+                                    shape[mode], drm->core_r1[k], ss.chain[k], st));
                 continue;
             }
             TTSK_TRY(sort_keys(ctx, nnz, idx_m, shape[mode], sb, st));
             ChainParams C;
             std::memset(&C, 0, sizeof(C));
             C.nnz = nnz; C.n_mu = shape[mode]; C.keyid = sb.keyid; C.offs = sb.offs;
-            C.core = drm->d_cores[k]; C.v_in = ss.chain[k - 1]; C.v_out = ss.chain[k];
+            C.core = drm->d_cores[k]; C.v_in = v_in; C.vin_idx = vin_idx; C.vin_stride = vin_stride; C.v_out = ss.chain[k];
             C.r_in = drm->core_r0[k]; C.r_out = drm->core_r1[k];
             TTSK_TRY(launch_chain(ctx, C, st));
         }
@@ -702,9 +712,22 @@ static int build_plan(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* shape
                 }
             } else {
                 std::memset(&S, 0, sizeof(S));
-                S.kind = SRC_ROWS;
                 S.r = drm->rank_max[bond] - drm->rank_min[bond];
                 const int k = drm->right ? d - 2 - bond : bond;  // chain level in DRM orientation
+                if (k == 0) {  // the first core (1, n, r) IS the table of this bond, indexed by its mode
+                    const int mode0 = drm->right ? d - 1 : 0;
+                    S.kind = SRC_TABLE;
+                    S.k = 1;
+                    S.modes[0] = mode0;
+                    S.strides[0] = 1;
+                    S.base = drm->d_cores[0] + drm->rank_min[bond];
+                    S.row_stride = drm->core_r1[0];
+                    S.col_stride = 1;
+                    S.span_bytes = shape[mode0] * (int64_t)drm->core_r1[0] * 8;
+                    ss.chain[0] = nullptr;
+                    continue;
+                }
+                S.kind = SRC_ROWS;
                 ss.chain[k] = (double*)ctx->ws_alloc(chunk * (int64_t)drm->core_r1[k] * 8);
                 if (!ss.chain[k]) { set_error("workspace too small for TT-DRM chain"); return TTSK_E_NOMEM; }
                 S.base = ss.chain[k] + drm->rank_min[bond];
@@ -738,7 +761,7 @@ static int64_t plan_workspace_bytes(int d, const int64_t* shape, int64_t nnz_tot
                 if (ok && ((rows <= table_rows_cap && rows * r * 8 <= ((int64_t)4 << 30)) || edge)) add(rows * r * 8);
             } else {
                 const int k = drm->right ? d - 2 - bond : bond;
-                add(chunk * (int64_t)drm->core_r1[k] * 8);
+                if (k > 0) add(chunk * (int64_t)drm->core_r1[k] * 8);
             }
         }
     }
@@ -977,7 +1000,7 @@ extern "C" int ttsk_ttdrm_sparse_step(ttsk_ctx* ctx, int64_t nnz, const int64_t*
     TTSK_ARG(ctx != nullptr, "ctx is NULL");
     TTSK_ARG(nnz >= 0 && r_out >= 1 && n >= 1 && (d_v_in == nullptr || r_in >= 1), "ttdrm step dims");
     TTSK_ARG(nnz == 0 || (d_idx_mu && d_core && d_v_out), "NULL pointer");
-    return ttdrm_step(ctx, nnz, (const long long*)d_idx_mu, d_v_in, r_in, d_core, n, r_out, d_v_out,
+    return ttdrm_step(ctx, nnz, (const long long*)d_idx_mu, d_v_in, r_in, nullptr, r_in, d_core, n, r_out, d_v_out,
                       (cudaStream_t)stream);
 }
 
