@@ -154,6 +154,17 @@ int ttsk_ttdrm_sparse_step(ttsk_ctx *ctx, int64_t nnz, const int64_t *d_idx_mu, 
                            int r_in, const double *d_core, int64_t n, int r_out, double *d_v_out,
                            void *stream);
 
+/* ---------------------------------------------------------------- TensorTrain input
+ * Streaming sketch of ONE TensorTrain summand with TensorTrainDRMs, ADDED to the packed sketch d_out
+ * (layout of ttsk_sparse_sketch).  Replaces, for TensorTrain input and method=streaming,
+ *   TensorTrainDRM.sketch_tt            tt_sketch/drm/tensor_train_drm.py:71-85
+ *   sketch_omega_tt / sketch_psi_tt      tt_sketch/sketching_methods/tensor_train_sketch.py:8-35
+ * as one fixed sequence of strided GEMMs (no per-GEMM host round trip).  h_tt_rank has d+1 entries
+ * (1, r_1, ..., r_{d-1}, 1); h_core_ptrs[k] is the DEVICE pointer of core k, (r_k, n_k, r_{k+1}) row-major. */
+int ttsk_tt_sketch(ttsk_ctx *ctx, int d, const int64_t *h_shape, const int32_t *h_tt_rank,
+                   const double *const *h_core_ptrs, const ttsk_drm *left, const ttsk_drm *right,
+                   double *d_out, void *stream);
+
 /* ---------------------------------------------------------------- dense building blocks
  * C[b] (M,N) = alpha * A[b] (M,K) @ B[b] (K,N) + beta * C[b], arbitrary element strides
  * (row stride, column stride) so transposes/slices are views.  Backs the TT / CP / dense

@@ -7,11 +7,15 @@
 // anyway) -- the work is bound by launch latency and by streaming the one large operand
 // once, so the kernel is a plain shared-memory tiled DFMA kernel whose grid is widened by
 // split-K until it covers the 148 SMs.
+#include <algorithm>
+
 #include "ttsk_common.cuh"
 
 namespace ttsk {
 
-constexpr int BM = 32, BN = 32, BK = 32;
+constexpr int BN = 32, BK = 32;  // the tile height BM is a template parameter: 64, or 16 for skinny M
+constexpr int PA = BK + 4;  // pitch of the A tile [m][k]: == 4 (mod 16) -> conflict-free a-fragment loads
+constexpr int PB = BN + 4;  // pitch of the B tile [k][n]: == 4 (mod 16) -> conflict-free b-fragment loads
 
 struct GemmArgs {
     long long M, N, K;
@@ -37,11 +41,24 @@ __global__ void scale_kernel(double* C, long long M, long long N, long long c_rs
     }
 }
 
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// A CTA computes a BM x 32 tile of C over its K range with FP64 tensor-core MMAs (DMMA.8x8x4).  BM = 64: warp w
+// owns rows 8w..8w+7 and the four 8-column tiles; BM = 16 (M <= 16: the DRM-rank-sized reductions over a huge K,
+// where a 64-row tile would spend 4/5 of the FP64 pipe on padding): warp w owns row tile w & 1, column tile w >> 1.
+// (The first version was a 2 x 2 register-tile DFMA kernel: one shared-memory load per FMA made it shared-memory
+// bound at ~0.7 TB/s of operand streaming.)
+template <int BM>
 __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
-    __shared__ double As[BK][BM + 1];
-    __shared__ double Bs[BK][BN + 1];
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 2 x 2 micro-tile each
+    constexpr int TPW = BM / 16;  // 8x8 output tiles per warp
+    __shared__ double As[BM * PA];
+    __shared__ double Bs[BK * PB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, q = lane & 3;
     const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * BN;
     const int split = blockIdx.z % g.splits;
     const long long batch = blockIdx.z / g.splits;
@@ -54,52 +71,83 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
 
     const bool a_kfast = (g.a_cs == 1);   // A row-major: k contiguous
     const bool b_nfast = (g.b_cs == 1);   // B row-major: n contiguous
-    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    const int rt = BM == 64 ? warp : (warp & 1);   // row tile of this warp
+    const int jc = BM == 64 ? 0 : (warp >> 1);     // its first column tile
+    double acc[TPW][2];
+#pragma unroll
+    for (int j = 0; j < TPW; j++) acc[j][0] = acc[j][1] = 0.0;
 
     for (long long k0 = k_begin; k0 < k_end; k0 += BK) {
+        const int kmax = (int)((k_end - k0 < BK) ? k_end - k0 : BK);
+        // all global loads of the step are issued before the first shared-memory store (A / B are generic pointers:
+        // interleaved, every load would have to wait for the store before it)
+        constexpr int NA = BM / 8;  // A elements per thread
+        double ra[NA], rb[4];
+        // A tile: BM x BK elements; lanes run along the contiguous dimension
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < NA; i++) {
             int mm, kk;
             if (a_kfast) { kk = tid & 31; mm = (tid >> 5) + 8 * i; }
-            else         { mm = tid & 31; kk = (tid >> 5) + 8 * i; }
+            else if (BM == 64) { mm = (tid & 31) + 32 * (i & 1); kk = (tid >> 5) + 8 * (i >> 1); }
+            else { mm = tid & 15; kk = (tid >> 4) + 16 * i; }
             const long long m = m0 + mm, k = k0 + kk;
-            As[kk][mm] = (m < g.M && k < k_end) ? A[m * g.a_rs + k * g.a_cs] : 0.0;
+            ra[i] = (m < g.M && kk < kmax) ? __ldg(A + m * g.a_rs + k * g.a_cs) : 0.0;
+        }
+        // B tile: BK x BN = 1024 elements, 4 per thread
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
             int nn, kb;
             if (b_nfast) { nn = tid & 31; kb = (tid >> 5) + 8 * i; }
             else         { kb = tid & 31; nn = (tid >> 5) + 8 * i; }
             const long long n = n0 + nn, k2 = k0 + kb;
-            Bs[kb][nn] = (n < g.N && k2 < k_end) ? B[k2 * g.b_rs + n * g.b_cs] : 0.0;
+            rb[i] = (n < g.N && kb < kmax) ? __ldg(B + k2 * g.b_rs + n * g.b_cs) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NA; i++) {
+            int mm, kk;
+            if (a_kfast) { kk = tid & 31; mm = (tid >> 5) + 8 * i; }
+            else if (BM == 64) { mm = (tid & 31) + 32 * (i & 1); kk = (tid >> 5) + 8 * (i >> 1); }
+            else { mm = tid & 15; kk = (tid >> 4) + 16 * i; }
+            As[mm * PA + kk] = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int nn, kb;
+            if (b_nfast) { nn = tid & 31; kb = (tid >> 5) + 8 * i; }
+            else         { kb = tid & 31; nn = (tid >> 5) + 8 * i; }
+            Bs[kb * PB + nn] = rb[i];
         }
         __syncthreads();
+        const int ksteps = (kmax + 3) >> 2;
+        for (int s = 0; s < ksteps; s++) {
+            const double a = As[(8 * rt + gq) * PA + 4 * s + q];
 #pragma unroll
-        for (int kk = 0; kk < BK; kk++) {
-            const double a0 = As[kk][ty], a1 = As[kk][ty + 16];
-            const double b0 = Bs[kk][tx], b1 = Bs[kk][tx + 16];
-            acc[0][0] = fma(a0, b0, acc[0][0]);
-            acc[0][1] = fma(a0, b1, acc[0][1]);
-            acc[1][0] = fma(a1, b0, acc[1][0]);
-            acc[1][1] = fma(a1, b1, acc[1][1]);
+            for (int j = 0; j < TPW; j++) dmma884(acc[j][0], acc[j][1], a, Bs[(4 * s + q) * PB + 8 * (jc + j) + gq]);
         }
         __syncthreads();
     }
+    const long long m = m0 + 8 * rt + gq;
+    if (m < g.M) {
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < TPW; j++)
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const long long m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
-            if (m < g.M && n < g.N) {
-                double* p = C + m * g.c_rs + n * g.c_cs;
-                const double v = g.alpha * acc[i][j];
-                if (g.use_atomic) atomicAdd(p, v);
-                else *p = (g.beta == 0.0) ? v : v + g.beta * (*p);
+            for (int e = 0; e < 2; e++) {
+                const long long n = n0 + 8 * (jc + j) + 2 * q + e;
+                if (n < g.N) {
+                    double* p = C + m * g.c_rs + n * g.c_cs;
+                    const double v = g.alpha * acc[j][e];
+                    if (g.use_atomic) atomicAdd(p, v);
+                    else *p = (g.beta == 0.0) ? v : v + g.beta * (*p);
+                }
             }
-        }
+    }
 }
 
 int gemm_launch(ttsk_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t a_rs,
                 int64_t a_cs, const double* B, int64_t b_rs, int64_t b_cs, double beta, double* C, int64_t c_rs,
                 int64_t c_cs, int64_t batch, int64_t a_bs, int64_t b_bs, int64_t c_bs, cudaStream_t st) {
     if (M <= 0 || N <= 0 || batch <= 0) return TTSK_OK;
+    const int BM = M <= 32 ? 16 : 64;  // rank-sized M: short tiles waste less of the FP64 pipe on padding
     const long long tm = (M + BM - 1) / BM, tn = (N + BN - 1) / BN;
     TTSK_ARG(tm <= 65535, "gemm: M too large for grid.y (reshape the problem)");
     GemmArgs g;
@@ -107,10 +155,10 @@ int gemm_launch(ttsk_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, co
     g.A = A; g.a_rs = a_rs; g.a_cs = a_cs; g.a_bs = a_bs;
     g.B = B; g.b_rs = b_rs; g.b_cs = b_cs; g.b_bs = b_bs;
     g.C = C; g.c_rs = c_rs; g.c_cs = c_cs; g.c_bs = c_bs;
-    // widen the grid with split-K until ~2 CTAs per SM
+    // widen the grid with split-K until ~4 CTAs per SM
     long long tiles = tm * tn * batch;
     long long splits = 1;
-    const long long target = 2LL * ctx->sm_count;
+    const long long target = 4LL * ctx->sm_count;
     if (tiles < target && K > 4 * BK) {
         splits = (target + tiles - 1) / tiles;
         const long long max_splits = (K + 4 * BK - 1) / (4 * BK);
@@ -135,7 +183,8 @@ int gemm_launch(ttsk_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, co
         }
     }
     dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)(batch * splits));
-    gemm_kernel<<<grid, 256, 0, st>>>(g);
+    if (BM == 16) gemm_kernel<16><<<grid, 256, 0, st>>>(g);
+    else gemm_kernel<64><<<grid, 256, 0, st>>>(g);
     TTSK_LAUNCHED(ctx);
     return TTSK_OK;
 }

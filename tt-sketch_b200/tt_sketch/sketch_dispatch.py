@@ -212,6 +212,25 @@ def _fused_sparse(X: SparseTensor, left_drm: DRM, right_drm: DRM, packed, accumu
     del lkeep, rkeep
 
 
+def _fused_tt(X: TensorTrain, left_drm: DRM, right_drm: DRM, packed):
+    """One C call for a TensorTrain summand under TT DRMs (ttsk_tt_sketch): the same GEMMs as
+    TensorTrainDRM.sketch_tt_device + omega_tt_device / psi_tt_device, without a host round trip each."""
+    from ctypes import c_void_p
+
+    cores = [c if c.is_contiguous() else c.contiguous() for c in X.device()["cores"]]
+    ld, lkeep = drm_descriptor(left_drm)
+    rd, rkeep = drm_descriptor(right_drm)
+    ptrs = (c_void_p * len(cores))(*[c.data_ptr() for c in cores])
+    be.check(be.lib().ttsk_tt_sketch(be.ctx(), X.ndim, be.as_i64(X.shape), be.as_i32((1,) + tuple(X.rank) + (1,)), ptrs,
+                                     byref(ld), byref(rd), be.ptr(packed), be.stream()))
+    del lkeep, rkeep, cores
+
+
+def _fusable_tt(X: Tensor, left_drm: DRM, right_drm: DRM) -> bool:
+    return (isinstance(X, TensorTrain) and type(left_drm) is TensorTrainDRM and type(right_drm) is TensorTrainDRM
+            and tuple(left_drm.shape) == tuple(X.shape) == tuple(right_drm.shape))
+
+
 def _fusable(X: Tensor, left_drm: DRM, right_drm: DRM) -> bool:
     return (isinstance(X, SparseTensor) and type(left_drm) in (SparseGaussianDRM, TensorTrainDRM)
             and type(right_drm) in (SparseGaussianDRM, TensorTrainDRM)
@@ -236,6 +255,9 @@ def streaming_sketch_device(tensor: Tensor, left_drm: DRM, right_drm: DRM, packe
             if tuple(left_drm.shape) != shape or tuple(right_drm.shape) != shape:
                 raise ValueError(f"Shape {left_drm.shape} of DRM doesn't match tensor's shape {shape}")
             _fused_sparse(X, left_drm, right_drm, packed, accumulate=True)
+            continue
+        if _fusable_tt(X, left_drm, right_drm):
+            _fused_tt(X, left_drm, right_drm, packed)
             continue
         _check_supported(X, left_drm)
         _check_supported(X, right_drm)
