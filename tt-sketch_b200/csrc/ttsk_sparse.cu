@@ -284,11 +284,22 @@ __global__ void __launch_bounds__(256) ttdrm_chain_kernel(const ChainParams C) {
                 double acc[NJ][2];
 #pragma unroll
                 for (int j = 0; j < NJ; j++) acc[j][0] = acc[j][1] = 0.0;
-                for (int kk = 0; kk < ksteps; kk++) {
-                    const int k = 4 * kk + q;
-                    const double a = (valid && k < C.r_in) ? __ldg(vin + k) : 0.0;
+                // input-row fragments four k-steps at a time (independent loads in flight), then their MMAs
+                for (int k0 = 0; k0 < ksteps; k0 += 4) {
+                    double a[4];
 #pragma unroll
-                    for (int j = 0; j < NJ; j++) dmma(acc[j][0], acc[j][1], a, Gs[k * C.pitch + 8 * j + g]);
+                    for (int u = 0; u < 4; u++) {
+                        const int k = 4 * (k0 + u) + q;
+                        a[u] = (k0 + u < ksteps && valid && k < C.r_in) ? __ldg(vin + k) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (k0 + u < ksteps) {
+                            const int k = 4 * (k0 + u) + q;
+#pragma unroll
+                            for (int j = 0; j < NJ; j++) dmma(acc[j][0], acc[j][1], a[u], Gs[k * C.pitch + 8 * j + g]);
+                        }
+                    }
                 }
                 if (valid) {
                     double* vout = C.v_out + id * C.r_out;
@@ -352,6 +363,12 @@ static int launch_pass(ttsk_ctx* ctx, PassParams& P, bool has_x, cudaStream_t st
 struct SortBufs {
     int* hist; int* offs; int* cursor;
     int* cta_cnt;  // per-CTA key counts / range starts of the two-level scatter
+    // TT DRMs bucket a mode up to three times (chain level of either side + the mode pass): with n_modes > 0 every
+    // mode keeps its own sorted words / segment starts for the chunk and is bucketed once
+    int n_modes = 0;
+    unsigned long long* keyid_m[TTSK_MAX_ORDER];
+    int* offs_m[TTSK_MAX_ORDER];
+    bool sorted_m[TTSK_MAX_ORDER];
     unsigned long long* keyid;
     unsigned* recs;
     int rec_words;
@@ -359,11 +376,22 @@ struct SortBufs {
 static int rec_words_for(int d) { return d <= 0 ? 0 : (int)align_up(2 + d, 8); }
 constexpr int kMaxSortCtas = 2 * 160;  // the two-level scatter runs two CTAs per SM
 static int64_t cta_cnt_bytes(int64_t n_max) { return n_max <= kLocalBins ? (int64_t)kMaxSortCtas * n_max * 4 : 256; }
-static int64_t sortbufs_bytes(int64_t n_max, int64_t chunk, int d) {
+static int64_t sortbufs_bytes(int64_t n_max, int64_t chunk, int d, int per_mode = 0) {
     return 3 * align_up((n_max + 1) * 4, 256) + align_up(chunk * 8, 256) + align_up(chunk * 4 * rec_words_for(d), 256) +
-           align_up(cta_cnt_bytes(n_max), 256) + 2048;
+           align_up(cta_cnt_bytes(n_max), 256) + 2048 +
+           (per_mode ? (int64_t)d * (align_up(chunk * 8, 256) + align_up((n_max + 1) * 4, 256)) : 0);
 }
-static int carve_sortbufs(ttsk_ctx* ctx, SortBufs& sb, int64_t n_max, int64_t chunk, int d) {
+static int carve_sortbufs(ttsk_ctx* ctx, SortBufs& sb, int64_t n_max, int64_t chunk, int d, int per_mode = 0) {
+    sb.n_modes = per_mode ? d : 0;
+    for (int m = 0; m < sb.n_modes; m++) {
+        sb.keyid_m[m] = (unsigned long long*)ctx->ws_alloc(chunk * 8);
+        sb.offs_m[m] = (int*)ctx->ws_alloc((n_max + 1) * 4);
+        sb.sorted_m[m] = false;
+        if (!sb.keyid_m[m] || !sb.offs_m[m]) {
+            set_error("workspace carve failed (per-mode sort buffers)");
+            return TTSK_E_NOMEM;
+        }
+    }
     sb.rec_words = rec_words_for(d);
     sb.recs = sb.rec_words ? (unsigned*)ctx->ws_alloc(chunk * 4 * sb.rec_words) : nullptr;
     if (sb.rec_words && !sb.recs) {
@@ -384,7 +412,13 @@ static int carve_sortbufs(ttsk_ctx* ctx, SortBufs& sb, int64_t n_max, int64_t ch
 
 // bucket the chunk by the index row `key_idx`: sb.keyid receives (key << 32 | id) in sorted order
 static int sort_keys(ttsk_ctx* ctx, int64_t nnz, const long long* key_idx, int64_t n_mu, SortBufs& sb,
-                     cudaStream_t st) {
+                     cudaStream_t st, int mode = -1) {
+    if (mode >= 0 && mode < sb.n_modes) {
+        sb.keyid = sb.keyid_m[mode];
+        sb.offs = sb.offs_m[mode];
+        if (sb.sorted_m[mode]) return TTSK_OK;  // this chunk is already bucketed by this mode
+        sb.sorted_m[mode] = true;
+    }
     long long blocks = (nnz + 255) / 256;
     if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
     long long block_len = (nnz + 2LL * ctx->sm_count - 1) / (2LL * ctx->sm_count);
@@ -535,6 +569,7 @@ struct SparsePlan {
 
 static int64_t chunk_bytes_per_nnz(int d, const ttsk_drm* left, const ttsk_drm* right) {
     int64_t b = 8 + 4 * rec_words_for(d);  // sorted (key, id) words + packed records
+    if (left->kind == TTSK_DRM_TT || right->kind == TTSK_DRM_TT) b += 8LL * d;  // per-mode sorted words
     if (left->kind == TTSK_DRM_TT)
         for (int k = 1; k < d - 1; k++) b += 8LL * left->core_r1[k];
     if (right->kind == TTSK_DRM_TT)
@@ -547,6 +582,7 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
                         const ttsk_drm* right, double* out, SortBufs& sb, cudaStream_t st) {
     if (nnz <= 0) return TTSK_OK;
     const SketchLayout& lay = pl.lay;
+    for (int m = 0; m < sb.n_modes; m++) sb.sorted_m[m] = false;
     // TT-DRM chains for this chunk (tensor_train_drm.py:60-69): level 0 is a row gather of the first
     // core; every further level is one bucketed pass over the nonzeros sorted by that level's mode
     for (int side = 0; side < 2; side++) {
@@ -568,7 +604,7 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
                                     shape[mode], drm->core_r1[k], ss.chain[k], st));
                 continue;
             }
-            TTSK_TRY(sort_keys(ctx, nnz, idx_m, shape[mode], sb, st));
+            TTSK_TRY(sort_keys(ctx, nnz, idx_m, shape[mode], sb, st, mode));
             ChainParams C;
             std::memset(&C, 0, sizeof(C));
             C.nnz = nnz; C.n_mu = shape[mode]; C.keyid = sb.keyid; C.offs = sb.offs;
@@ -627,7 +663,7 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
             TTSK_TRY(launch_last_mode_unbucketed(ctx, P, st, &flat_done));
             if (flat_done) { TTSK_TRY(mark(1)); continue; }
         }
-        TTSK_TRY(sort_keys(ctx, nnz, idx_rows[mu], shape[mu], sb, st));
+        TTSK_TRY(sort_keys(ctx, nnz, idx_rows[mu], shape[mu], sb, st, mu));
         P.keyid = sb.keyid;
         P.offs = sb.offs;
         TTSK_TRY(mark(0));
@@ -746,7 +782,7 @@ static int64_t plan_workspace_bytes(int d, const int64_t* shape, int64_t nnz_tot
     int64_t bytes = 0;
     auto add = [&](int64_t b) { bytes = align_up(bytes, 256) + b; };
     add(sketch_elems * 8);                  // temp sketch when accumulating
-    add(sortbufs_bytes(n_max, chunk, d));   // hist/offs/cursor + sorted (key, id) words + packed records
+    add(sortbufs_bytes(n_max, chunk, d, left->kind == TTSK_DRM_TT || right->kind == TTSK_DRM_TT));   // hist/offs/cursor + sorted (key, id) words + packed records
     const int64_t table_rows_cap = std::max<int64_t>(nnz_total, 1);  // a table row is cheaper than two on-the-fly rows and is cached
     for (int side = 0; side < 2; side++) {
         const ttsk_drm* drm = side == 0 ? left : right;
@@ -844,7 +880,7 @@ extern "C" int ttsk_sparse_sketch(ttsk_ctx* ctx, int d, const int64_t* h_shape, 
     int64_t n_max = 0;
     for (int mu = 0; mu < d; mu++) n_max = std::max<int64_t>(n_max, h_shape[mu]);
     SortBufs sb;
-    TTSK_TRY(carve_sortbufs(ctx, sb, n_max, chunk, d));
+    TTSK_TRY(carve_sortbufs(ctx, sb, n_max, chunk, d, left->kind == TTSK_DRM_TT || right->kind == TTSK_DRM_TT));
     if (!tmp) {
         set_error("workspace carve failed");
         return TTSK_E_NOMEM;
@@ -928,7 +964,7 @@ static int sparse_sketch_from_host(ttsk_ctx* ctx, int d, const int64_t* h_shape,
     int64_t n_max = 0;
     for (int mu = 0; mu < d; mu++) n_max = std::max<int64_t>(n_max, h_shape[mu]);
     SortBufs sb;
-    TTSK_TRY(carve_sortbufs(ctx, sb, n_max, chunk, d));
+    TTSK_TRY(carve_sortbufs(ctx, sb, n_max, chunk, d, left->kind == TTSK_DRM_TT || right->kind == TTSK_DRM_TT));
     if (!d_stage[0] || !d_stage[1] || !sk) {
         set_error("workspace carve failed");
         return TTSK_E_NOMEM;
