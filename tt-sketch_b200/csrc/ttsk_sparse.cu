@@ -8,19 +8,26 @@
 //
 // Design:
 //   * the reference materialises (r x nnz) DRM rows for every bond and scans all nonzeros once
-//     per slice j of every mode (O(n_mu * nnz)).  Here nonzeros are bucketed once per mode
-//     (counting sort -> permutation + sorted keys) and a mode pass walks the buckets: a CTA
-//     takes a contiguous piece of the sorted order, forms for TN nonzeros at a time the tiles
+//     per slice j of every mode (O(n_mu * nnz)).  Here the chunk is packed into 32-byte records,
+//     bucketed once per mode (counting sort -> sorted (key, id) words) and a mode pass walks the
+//     buckets tile by tile, forming
 //         At (rA x TN) = v_p * L_{mu-1}(p),  Bt (rB x TN) = R_mu(p),  Xt (rX x TN) = R_{mu-1}(p)
-//     in shared memory and accumulates  Psi_mu[:, j, :] += At Bt^T  (and Omega_{mu-1} += At Xt^T)
-//     in registers with mma.sync.m8n8k4.f64, writing each slice once per piece.
+//     in shared memory and accumulating  Psi_mu[:, j, :] += At Bt^T  (and Omega_{mu-1} += At Xt^T)
+//     in registers with mma.sync.m8n8k4.f64, flushing a slice when the key changes.
+//   * the pass kernels (ttsk_sparse_pass.cuh, instantiated in ttsk_sparse_pass_x0/x1.cu) are
+//     warp-specialised and persistent: producer warps stage tiles and launch asynchronous row
+//     copies into an mbarrier ring, consumer warps generate / multiply their own rows without CTA
+//     barriers; a segment-GEMM form and an unbucketed last-mode form replace the per-nonzero MMAs
+//     when the right factor is a small table or absent.
 //   * tile entries come from a "source": hash-seeded Gaussian generated on the fly (never
-//     stored in HBM), a small prefix table of the same generator gathered through L2 when the
-//     prefix index space is much smaller than nnz, or rows of a per-nonzero buffer (TT-DRM
-//     chain products / user-supplied rows).
+//     stored in HBM), a prefix table of the same generator (or the first core of a TT DRM) gathered
+//     through L2 when the prefix index space is not larger than nnz, or rows of a per-nonzero
+//     buffer (TT-DRM chain products / user-supplied rows).
 //   * the tail branch of ndtri (27% of draws) is deferred to a dense second phase so the
 //     central branch runs without the tail's divergence.
 //   * edge bonds need no per-nonzero work:  Omega_0 = L_0^T Psi_0,  Omega_{d-2} = Psi_{d-1} R_{d-2}^T.
+//
+// This file: bucketing kernels, TT-DRM chain kernels, host-side planning, the C entry points.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
