@@ -50,6 +50,40 @@ def test_linearity_and_split_full_size_stream():
         assert _close(a, b)
 
 
+def test_host_streaming_call_equals_device_call():
+    """ttsk_sparse_sketch_host (graduated chunks through pinned staging: every chunk buckets, passes and flushes its
+    own segments) == ttsk_sparse_sketch on device-resident COO: two different tilings of the same sums, including
+    the segment-GEMM and the unbucketed last-mode forms (shape (3000, 3000, 40, 50), 3e6 nonzeros -> chunks of 1e6 and 2e6)."""
+    import torch
+    from ctypes import byref
+    from tt_sketch import _backend as be
+    from tt_sketch.drm import SparseGaussianDRM
+    from tt_sketch.sketch_container import SketchContainer
+    from tt_sketch.sketch_dispatch import drm_descriptor
+
+    shape = (3000, 3000, 40, 50)
+    lr, rr = (20,) * 3, (40,) * 3
+    nnz = 3_000_000
+    X = _sparse(shape, nnz, 11)
+    L, R = _drms(shape, lr, rr, SparseGaussianDRM, SparseGaussianDRM)
+    ld, _k1 = drm_descriptor(L)
+    rd, _k2 = drm_descriptor(R)
+    _, total = SketchContainer.layout(shape, lr, rr)
+    lib, ctx = be.lib(), be.ctx()
+    d_idx, d_val = torch.from_numpy(X.indices).cuda(), torch.from_numpy(X.entries).cuda()
+    out = torch.empty(total, dtype=torch.float64, device="cuda")
+    sg0 = lib.ttsk_sg_pass_count(ctx)
+    be.check(lib.ttsk_sparse_sketch(ctx, 4, be.as_i64(shape), nnz, be.ptr(d_idx), d_idx.stride(0), be.ptr(d_val),
+                                    byref(ld), byref(rd), be.ptr(out), 0, be.stream()))
+    torch.cuda.synchronize()
+    assert lib.ttsk_sg_pass_count(ctx) >= sg0 + 2, "segment-GEMM / unbucketed forms were not taken"
+    h_idx, h_val = torch.from_numpy(X.indices).pin_memory(), torch.from_numpy(X.entries).pin_memory()
+    h_out = torch.empty(total, dtype=torch.float64).pin_memory()
+    be.check(lib.ttsk_sparse_sketch_host(ctx, 4, be.as_i64(shape), nnz, h_idx.data_ptr(), h_idx.stride(0),
+                                         h_val.data_ptr(), byref(ld), byref(rd), h_out.data_ptr(), 0))
+    assert _close(h_out.numpy(), out.cpu().numpy(), tol=1e-11)
+
+
 @pytest.mark.parametrize("kind", ["gauss", "tt"])
 def test_blocked_equals_unblocked_and_rank_increase(kind):
     from tt_sketch.drm import SparseGaussianDRM, TensorTrainDRM
