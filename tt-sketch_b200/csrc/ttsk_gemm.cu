@@ -128,18 +128,33 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
     }
     const long long m = m0 + 8 * rt + gq;
     if (m < g.M) {
+        // the two accumulators of a lane are adjacent columns: one 16-byte read-modify-write when C allows it
+        const bool vec = !g.use_atomic && g.c_cs == 1 && (g.c_rs & 1) == 0 && (g.c_bs & 1) == 0 &&
+                         (reinterpret_cast<unsigned long long>(g.C) & 15ull) == 0;
 #pragma unroll
-        for (int j = 0; j < TPW; j++)
+        for (int j = 0; j < TPW; j++) {
+            const long long n = n0 + 8 * (jc + j) + 2 * q;
+            if (vec && n + 1 < g.N) {
+                double2* p = reinterpret_cast<double2*>(C + m * g.c_rs + n);
+                double2 v = make_double2(g.alpha * acc[j][0], g.alpha * acc[j][1]);
+                if (g.beta != 0.0) {
+                    const double2 old = *p;
+                    v.x += g.beta * old.x;
+                    v.y += g.beta * old.y;
+                }
+                *p = v;
+                continue;
+            }
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const long long n = n0 + 8 * (jc + j) + 2 * q + e;
-                if (n < g.N) {
-                    double* p = C + m * g.c_rs + n * g.c_cs;
+                if (n + e < g.N) {
+                    double* p = C + m * g.c_rs + (n + e) * g.c_cs;
                     const double v = g.alpha * acc[j][e];
                     if (g.use_atomic) atomicAdd(p, v);
                     else *p = (g.beta == 0.0) ? v : v + g.beta * (*p);
                 }
             }
+        }
     }
 }
 
