@@ -151,3 +151,27 @@ def test_entry_point_validation_without_gpu():
         orthogonal_sketch(tt, (3, 3), (2, 4))
     with pytest.raises(ValueError):
         blocked_stream_sketch(tt, object(), object(), [], [])
+
+
+def test_fused_path_selection_is_host_logic_only():
+    """Which summands take the single-call device paths (ttsk_sparse_sketch / ttsk_tt_sketch) is decided from the
+    tensor and DRM types alone, without touching the device."""
+    from tt_sketch.drm import SparseGaussianDRM, TensorTrainDRM
+    from tt_sketch.sketch_dispatch import _fusable, _fusable_tt
+    from tt_sketch.tensor import CPTensor, SparseTensor, TensorTrain
+
+    shape = (6, 5, 4)
+    tt = TensorTrain.random(shape, 2, seed=1)
+    cp = CPTensor.random(shape, 2, seed=1)
+    sp = SparseTensor(shape, np.zeros((3, 1), dtype=np.int64), np.ones(1))
+    tl = TensorTrainDRM((2, 2), shape=shape, transpose=False, seed=1)
+    tr = TensorTrainDRM((3, 3), shape=shape, transpose=True, seed=2)
+    gl = SparseGaussianDRM((2, 2), shape=shape, transpose=False, seed=1)
+    gr = SparseGaussianDRM((3, 3), shape=shape, transpose=True, seed=2)
+    assert _fusable_tt(tt, tl, tr)
+    assert not _fusable_tt(cp, tl, tr) and not _fusable_tt(sp, tl, tr)
+    assert not _fusable_tt(tt, gl, gr)  # a Gaussian DRM has no TensorTrain contraction (reference: sketch_sparse only)
+    assert _fusable(sp, gl, gr) and _fusable(sp, tl, tr) and _fusable(sp, gl, tr)
+    assert not _fusable(tt, tl, tr)
+    big = TensorTrainDRM((70, 70), shape=(80, 80, 80), transpose=False, seed=1)
+    assert not _fusable(SparseTensor((80, 80, 80), np.zeros((3, 1), dtype=np.int64), np.ones(1)), big, big)  # rank > 64
