@@ -57,6 +57,15 @@ int ttsk_memset_zero(ttsk_ctx *ctx, void *d_ptr, int64_t bytes, void *stream);
 int ttsk_sync(ttsk_ctx *ctx, void *stream);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t ttsk_launch_count(ttsk_ctx *ctx);
+/* The library keeps two grow-only device allocations per context: a workspace arena and a cache of
+ * Gaussian-DRM prefix tables (DRM state: reused by later sketches with the same DRM, like the
+ * reference keeps TT-DRM cores, tt_sketch/drm/tensor_train_drm.py:52-56).  ttsk_set_table_cache_cap
+ * bounds the cache (default 6 GiB; least recently used tables are dropped, never one the running
+ * call uses; bonds whose table does not fit are generated on the fly instead);
+ * ttsk_trim releases both allocations (synchronises). */
+int ttsk_set_table_cache_cap(ttsk_ctx *ctx, int64_t bytes);
+int64_t ttsk_table_cache_bytes(ttsk_ctx *ctx);
+int ttsk_trim(ttsk_ctx *ctx);
 /* Milliseconds spent in the sketch kernels of the most recent ttsk_sparse_sketch* call,
  * measured with CUDA events on the launching stream (synchronises). */
 int ttsk_last_kernel_ms(ttsk_ctx *ctx, double *ms_total, double *ms_dominant);
@@ -78,6 +87,9 @@ int ttsk_lazy_gaussian(ttsk_ctx *ctx, const int64_t *d_idx, int64_t idx_row_stri
  * pairs (n pseudo-random pairs from `seed`, magnitudes 2^-30..2^10 and zero numerators) whose
  * quotient differs from CUDA's IEEE __ddiv_rn.  Must report 0.  Synchronous. */
 int ttsk_selftest_div(ttsk_ctx *ctx, int64_t n, uint64_t seed, uint64_t *h_mismatches);
+/* Same for the straight-line FP64 square root of the tail branch (operands 2^-8..2^12) against CUDA's
+ * IEEE __dsqrt_rn.  Must report 0.  Synchronous. */
+int ttsk_selftest_sqrt(ttsk_ctx *ctx, int64_t n, uint64_t seed, uint64_t *h_mismatches);
 
 /* ---------------------------------------------------------------- DRM descriptors
  * A dimension-reduction map in USER orientation (bond mu = 0..d-2).

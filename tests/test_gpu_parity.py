@@ -61,6 +61,17 @@ def test_straight_line_division_is_ieee():
     assert bad.value == 0
 
 
+def test_straight_line_sqrt_is_ieee():
+    """sqrt_rn_safe (the branch-free square root of the tail branch) == __dsqrt_rn on 2e8 operands."""
+    from ctypes import byref, c_uint64
+
+    from tt_sketch import _backend as be
+
+    bad = c_uint64(123)
+    be.check(be.lib().ttsk_selftest_sqrt(be.ctx(), 200_000_000, 20240918, byref(bad)))
+    assert bad.value == 0
+
+
 def test_ndtri_tail_and_edge_uniforms(oracle_lib):
     """The deferred tail branch is exercised by every sketch; here the Gaussian rows of a sliced
     DRM must equal the same columns of the unsliced one bit-for-bit (reference

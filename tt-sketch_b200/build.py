@@ -21,6 +21,8 @@ SOURCES = ["ttsk_sparse_pass_x0.cu", "ttsk_sparse_pass_x1.cu", "ttsk_api.cu", "t
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+if os.environ.get("TTSK_PROFILE"):  # profiling build: enables the TTSK_ABLATE / TTSK_L2_FETCH switches (never shipped)
+    FLAGS.append("-DTTSK_PROFILE")
 
 
 def _newer(target, deps):

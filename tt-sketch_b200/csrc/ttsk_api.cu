@@ -1,4 +1,5 @@
 // Context, memory and error plumbing of libttsk.so (C ABI in include/ttsk.h).
+#include <cstdlib>
 #include <cstring>
 
 #include "ttsk_common.cuh"
@@ -86,6 +87,9 @@ int ttsk_create(int device, ttsk_ctx** out) {
         ttsk::set_error("device %d is sm_%d%d; libttsk is built for sm_100a only", device, prop.major, prop.minor);
         return TTSK_E_NODEVICE;
     }
+#ifdef TTSK_PROFILE
+    if (getenv("TTSK_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(getenv("TTSK_L2_FETCH")));
+#endif
     ttsk_ctx* c = new ttsk_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
@@ -177,5 +181,25 @@ int ttsk_sync(ttsk_ctx* ctx, void* stream) {
     return TTSK_OK;
 }
 int64_t ttsk_launch_count(ttsk_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int ttsk_set_table_cache_cap(ttsk_ctx* ctx, int64_t bytes) {
+    TTSK_ARG(ctx != nullptr && bytes >= 0, "ttsk_set_table_cache_cap");
+    ctx->table_cap = bytes;
+    return TTSK_OK;
+}
+int64_t ttsk_table_cache_bytes(ttsk_ctx* ctx) { return ctx ? ctx->table_bytes : -1; }
+
+int ttsk_trim(ttsk_ctx* ctx) {
+    TTSK_ARG(ctx != nullptr, "ctx is NULL");
+    TTSK_CUDA(cudaSetDevice(ctx->device));
+    TTSK_CUDA(cudaDeviceSynchronize());
+    if (ctx->ws) TTSK_CUDA(cudaFree(ctx->ws));
+    ctx->ws = nullptr;
+    ctx->ws_bytes = ctx->ws_used = 0;
+    for (auto& t : ctx->tables) TTSK_CUDA(cudaFree(t.ptr));
+    ctx->tables.clear();
+    ctx->table_bytes = 0;
+    return TTSK_OK;
+}
 
 }  // extern "C"

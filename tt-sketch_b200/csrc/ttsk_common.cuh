@@ -72,9 +72,11 @@ struct ttsk_ctx {
     int n_pass_events = 0;
     bool timing = true;
     // prefix tables of Gaussian DRMs depend only on (seed, column range, rows): kept across calls
-    struct TableEntry { uint64_t seed; int rank_min, r; int64_t rows; double* ptr; int64_t bytes; cudaStream_t stream; };
-    std::vector<TableEntry> tables;
+    struct TableEntry { uint64_t seed; int rank_min, r; int64_t rows; double* ptr; int64_t bytes; cudaStream_t stream; int64_t pin_gen; };
+    std::vector<TableEntry> tables;  // least recently used first
     int64_t table_bytes = 0;
+    int64_t table_cap = (int64_t)6 << 30;
+    int64_t plan_gen = 0;  // generation id of the sparse plan being built: its tables are never evicted
 
     int ws_reserve(int64_t bytes);              // make the arena at least this large (may sync)
     void ws_reset() { ws_used = 0; }

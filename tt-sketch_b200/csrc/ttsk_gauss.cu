@@ -91,7 +91,33 @@ __global__ void selftest_div_kernel(long long n, unsigned long long seed, unsign
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// self-test: sqrt_rn_safe vs __dsqrt_rn on pseudo-random operands 2^-8 .. 2^12 (ndtri uses (4, 80))
+__global__ void selftest_sqrt_kernel(long long n, unsigned long long seed, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long h1 = hash64(seed + i);
+        const int ea = (int)((h1 >> 52) % 21) - 8;
+        const double a = ldexp(1.0 + uniform_from_hash(h1), ea);
+        const double want = __dsqrt_rn(a), got = sqrt_rn_safe(a);
+        if (__double_as_longlong(want) != __double_as_longlong(got)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace ttsk
+
+extern "C" int ttsk_selftest_sqrt(ttsk_ctx* ctx, int64_t n, uint64_t seed, uint64_t* h_mismatches) {
+    TTSK_ARG(ctx != nullptr && h_mismatches != nullptr && n >= 0, "selftest_sqrt");
+    unsigned long long* d = nullptr;
+    TTSK_CUDA(cudaMalloc((void**)&d, 8));
+    TTSK_CUDA(cudaMemset(d, 0, 8));
+    ttsk::selftest_sqrt_kernel<<<ctx->sm_count * 8, 256>>>(n, seed, d);
+    TTSK_LAUNCHED(ctx);
+    TTSK_CUDA(cudaMemcpy(h_mismatches, d, 8, cudaMemcpyDeviceToHost));
+    TTSK_CUDA(cudaFree(d));
+    return TTSK_OK;
+}
 
 extern "C" int ttsk_selftest_div(ttsk_ctx* ctx, int64_t n, uint64_t seed, uint64_t* h_mismatches) {
     TTSK_ARG(ctx != nullptr && h_mismatches != nullptr && n >= 0, "selftest_div");

@@ -682,33 +682,49 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
 
 // Prefix tables are a function of the DRM alone (seed, column range, number of rows), so they are
 // generated once per context and reused by later sketches with the same DRM (streaming updates,
-// blocked sketches, repeated calls).  Cache capped at 6 GB, oldest entries dropped first.
+// blocked sketches, repeated calls).  The cache is capped (ctx->table_cap, 6 GB by default); least
+// recently used entries are dropped first, but NEVER an entry the plan being built already uses
+// (entries are pinned with the plan's generation id).  When the cap cannot be met without that,
+// `*out` stays nullptr unless `must` is set (edge tables, which are small and always needed), and
+// the caller keeps generating that bond on the fly.
 static int cached_gauss_table(ttsk_ctx* ctx, int64_t rows, int rank_min, int r, uint64_t seed, double** out,
-                              cudaStream_t st) {
-    for (auto& t : ctx->tables)
+                              cudaStream_t st, bool must) {
+    *out = nullptr;
+    for (size_t i = 0; i < ctx->tables.size(); i++) {
+        auto& t = ctx->tables[i];
         if (t.seed == seed && t.rank_min == rank_min && t.r == r && t.rows == rows) {
             if (t.stream != st) TTSK_CUDA(cudaStreamSynchronize(t.stream));  // filled on another stream
             t.stream = st;
+            t.pin_gen = ctx->plan_gen;
             *out = t.ptr;
+            if (i + 1 != ctx->tables.size()) {  // most recently used entries live at the back
+                auto e = t;
+                ctx->tables.erase(ctx->tables.begin() + (long)i);
+                ctx->tables.push_back(e);
+            }
             return TTSK_OK;
         }
-    const int64_t bytes = rows * (int64_t)r * 8;
-    const int64_t cap = (int64_t)6 << 30;
-    while (!ctx->tables.empty() && ctx->table_bytes + bytes > cap) {
-        TTSK_CUDA(cudaDeviceSynchronize());
-        TTSK_CUDA(cudaFree(ctx->tables.front().ptr));
-        ctx->table_bytes -= ctx->tables.front().bytes;
-        ctx->tables.erase(ctx->tables.begin());
     }
+    const int64_t bytes = rows * (int64_t)r * 8;
+    bool synced = false;
+    for (size_t i = 0; i < ctx->tables.size() && ctx->table_bytes + bytes > ctx->table_cap;) {
+        if (ctx->tables[i].pin_gen == ctx->plan_gen) { i++; continue; }  // in use by the plan being built
+        if (!synced) { TTSK_CUDA(cudaDeviceSynchronize()); synced = true; }
+        TTSK_CUDA(cudaFree(ctx->tables[i].ptr));
+        ctx->table_bytes -= ctx->tables[i].bytes;
+        ctx->tables.erase(ctx->tables.begin() + (long)i);
+    }
+    if (ctx->table_bytes + bytes > ctx->table_cap && !must) return TTSK_OK;  // caller generates on the fly
     double* p = nullptr;
     cudaError_t e = cudaMalloc((void**)&p, (size_t)bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
+        if (!must) return TTSK_OK;
         set_error("DRM table allocation of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
         return TTSK_E_NOMEM;
     }
     TTSK_TRY(gauss_table_launch(ctx, rows, rank_min, r, seed, p, st));
-    ctx->tables.push_back({seed, rank_min, r, rows, p, bytes, st});
+    ctx->tables.push_back({seed, rank_min, r, rows, p, bytes, st, ctx->plan_gen});
     ctx->table_bytes += bytes;
     *out = p;
     return TTSK_OK;
@@ -723,6 +739,7 @@ static int build_plan(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* shape
         rR[mu] = right->rank_max[mu] - right->rank_min[mu];
     }
     make_layout(pl.lay, d, shape, rL, rR);
+    ctx->plan_gen++;  // tables fetched from here on are pinned until the next plan
     pl.n_max = 0;
     for (int mu = 0; mu < d; mu++) pl.n_max = std::max<int64_t>(pl.n_max, shape[mu]);
     pl.edge_L0 = nullptr;
@@ -741,10 +758,10 @@ static int build_plan(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* shape
                 const bool small = rows > 0 && rows <= table_rows_cap && rows * S.r * 8 <= table_bytes_cap;
                 if (small || (edge && rows > 0)) {
                     double* tab = nullptr;
-                    TTSK_TRY(cached_gauss_table(ctx, rows, S.rank_min, S.r, S.seed, &tab, st));
+                    TTSK_TRY(cached_gauss_table(ctx, rows, S.rank_min, S.r, S.seed, &tab, st, edge));
                     if (edge && side == 0) pl.edge_L0 = tab;
                     if (edge && side == 1) pl.edge_R = tab;
-                    if (small) {
+                    if (small && tab) {
                         // true (unwrapped) strides equal the wrapped ones because rows < 2^31
                         S.kind = SRC_TABLE;
                         S.base = tab;
@@ -800,8 +817,7 @@ static int64_t plan_workspace_bytes(int d, const int64_t* shape, int64_t nnz_tot
                 bool ok = true;
                 if (!drm->right) { for (int i = 0; i <= bond; i++) { rows *= shape[i]; if (rows >= ((int64_t)1 << 31)) { ok = false; break; } } }
                 else { for (int i = d - 1; i > bond; i--) { rows *= shape[i]; if (rows >= ((int64_t)1 << 31)) { ok = false; break; } } }
-                const bool edge = (side == 0 && bond == 0) || (side == 1 && bond == d - 2);
-                if (ok && ((rows <= table_rows_cap && rows * r * 8 <= ((int64_t)4 << 30)) || edge)) add(rows * r * 8);
+                (void)ok; (void)r; (void)table_rows_cap;  // prefix tables live in the context's table cache, not in the arena
             } else {
                 const int k = drm->right ? d - 2 - bond : bond;
                 if (k > 0) add(chunk * (int64_t)drm->core_r1[k] * 8);

@@ -53,9 +53,13 @@ SIGNATURES = {
     "ttsk_last_kernel_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "ttsk_last_pass_ms": (c_int, [c_void_p, POINTER(c_double), c_int, POINTER(c_int)]),
     "ttsk_sg_pass_count": (c_int64, [c_void_p]),
+    "ttsk_set_table_cache_cap": (c_int, [c_void_p, c_int64]),
+    "ttsk_table_cache_bytes": (c_int64, [c_void_p]),
+    "ttsk_trim": (c_int, [c_void_p]),
     "ttsk_lazy_gaussian": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, POINTER(c_int64), c_int, c_int,
                                    c_uint64, c_void_p, c_void_p]),
     "ttsk_selftest_div": (c_int, [c_void_p, c_int64, c_uint64, POINTER(c_uint64)]),
+    "ttsk_selftest_sqrt": (c_int, [c_void_p, c_int64, c_uint64, POINTER(c_uint64)]),
     "ttsk_sketch_size": (c_int64, [c_int, POINTER(c_int64), POINTER(c_int32), POINTER(c_int32)]),
     "ttsk_sparse_sketch": (c_int, [c_void_p, c_int, POINTER(c_int64), c_int64, c_void_p, c_int64, c_void_p,
                                    POINTER(TtskDrm), POINTER(TtskDrm), c_void_p, c_int, c_void_p]),

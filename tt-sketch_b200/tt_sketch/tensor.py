@@ -5,7 +5,7 @@ DenseTensor (:140), SparseTensor (:186), TensorTrain (:294), TensorSum (:612) an
 (:674).  Only what the sketching hot path and its tests need is provided; the tensor
 algebra that is not sketching (round, dot, gather, svdvals, orthogonalize, TuckerTensor) is
 out of scope.  Containers additionally cache device copies of their
-arrays (`.device()`), uploaded once and reused by every sketch.
+arrays (`.device()`), keyed by CUDA device and by the identity of the host arrays.
 """
 from __future__ import annotations
 
@@ -75,13 +75,36 @@ class Tensor(ABC):
             err /= float(np.sqrt(np.prod(self.shape)))
         return err
 
-    # ---- device residency (upload once; inputs are immutable by contract) ----
+    # ---- device residency ----
+    # The upload is cached per (CUDA device, identity of the host arrays).  Replacing an array
+    # (`t.entries = ...`, `tt[i] = core`, `tt.cores = [...]`) or switching the current device is
+    # detected and triggers a fresh upload, like the reference always reads the current arrays.
+    # Editing an array IN PLACE (`t.entries[3] = 0`) cannot be seen without hashing the data:
+    # call `invalidate_device()` after such an edit.
     def device(self):
-        cache = self.__dict__.get("_dev")
-        if cache is None:
-            cache = self._upload()
-            self.__dict__["_dev"] = cache
-        return cache
+        from tt_sketch import _backend as be
+
+        key = (be.device_index(), self._host_arrays_id())
+        if self.__dict__.get("_dev") is None or self.__dict__.get("_dev_key") != key:
+            self.__dict__["_dev"] = self._upload()
+            self.__dict__["_dev_key"] = key
+        return self.__dict__["_dev"]
+
+    def invalidate_device(self) -> None:
+        self.__dict__.pop("_dev", None)
+        self.__dict__.pop("_dev_key", None)
+
+    def _device_if_current(self):
+        """The cached upload if it still matches the host arrays and the current device, else None."""
+        from tt_sketch import _backend as be
+
+        if self.__dict__.get("_dev") is not None and \
+                self.__dict__.get("_dev_key") == (be.device_index(), self._host_arrays_id()):
+            return self.__dict__["_dev"]
+        return None
+
+    def _host_arrays_id(self):
+        raise NotImplementedError
 
     def _upload(self):
         raise NotImplementedError
@@ -116,6 +139,9 @@ class DenseTensor(Tensor):
 
     def __repr__(self) -> str:
         return f"<Dense tensor of shape {self.shape} at {hex(id(self))}>"
+
+    def _host_arrays_id(self):
+        return (id(self.data),)
 
     def _upload(self):
         from tt_sketch import _backend as be
@@ -190,13 +216,19 @@ class SparseTensor(Tensor):
             raise ValueError("sparse index out of range for the tensor shape")
         self.__dict__["_checked"] = True
 
+    def _host_arrays_id(self):
+        return (id(self.indices), id(self.entries))
+
     def _upload(self):
         from tt_sketch import _backend as be
 
+        self.__dict__.pop("_checked", None) if self.__dict__.get("_checked_for") != self._host_arrays_id() else None
         self.check_indices()
+        self.__dict__["_checked_for"] = self._host_arrays_id()
         parent = self.__dict__.get("_dev_parent")
-        if parent is not None and "_dev" in parent.__dict__:  # derive on the device, no second upload
-            pd = parent.__dict__["_dev"]
+        pd = parent._device_if_current() if parent is not None else None
+        # derive on the device (no second upload) when this is still the transpose of the parent's current arrays
+        if pd is not None and self.entries is parent.entries and getattr(self.indices, "base", None) is parent.indices:
             return {"indices": pd["indices"].flip(0), "entries": pd["entries"]}
         return {"indices": be.to_device(self.indices, np.int64), "entries": be.to_device(self.entries, np.float64)}
 
@@ -270,12 +302,17 @@ class TensorTrain(Tensor):
     def __repr__(self) -> str:
         return f"<Tensor train of shape {self.shape} with rank {self.rank} at {hex(id(self))}>"
 
+    def _host_arrays_id(self):
+        return tuple(id(c) for c in self.cores)
+
     def _upload(self):
         from tt_sketch import _backend as be
 
         parent = self.__dict__.get("_dev_parent")
-        if parent is not None and "_dev" in parent.__dict__:
-            return {"cores": [c.permute(2, 1, 0).contiguous() for c in reversed(parent.__dict__["_dev"]["cores"])]}
+        pd = parent._device_if_current() if parent is not None else None
+        if pd is not None and len(parent.cores) == len(self.cores) and \
+                all(getattr(c, "base", None) is pc for c, pc in zip(self.cores, reversed(parent.cores))):
+            return {"cores": [c.permute(2, 1, 0).contiguous() for c in reversed(pd["cores"])]}
         return {"cores": [be.to_device(c, np.float64) for c in self.cores]}
 
 
@@ -320,12 +357,17 @@ class CPTensor(Tensor):
     def __repr__(self) -> str:
         return f"<CP tensor of shape {self.shape} and rank {self.rank} at {hex(id(self))}>"
 
+    def _host_arrays_id(self):
+        return tuple(id(c) for c in self.cores)
+
     def _upload(self):
         from tt_sketch import _backend as be
 
         parent = self.__dict__.get("_dev_parent")
-        if parent is not None and "_dev" in parent.__dict__:
-            return {"cores": list(reversed(parent.__dict__["_dev"]["cores"]))}
+        pd = parent._device_if_current() if parent is not None else None
+        if pd is not None and len(parent.cores) == len(self.cores) and \
+                all(c is pc for c, pc in zip(self.cores, reversed(parent.cores))):
+            return {"cores": list(reversed(pd["cores"]))}
         return {"cores": [be.to_device(c, np.float64) for c in self.cores]}
 
 
