@@ -65,6 +65,9 @@ int64_t ttsk_launch_count(ttsk_ctx *ctx);
  * ttsk_trim releases both allocations (synchronises). */
 int ttsk_set_table_cache_cap(ttsk_ctx *ctx, int64_t bytes);
 int64_t ttsk_table_cache_bytes(ttsk_ctx *ctx);
+/* Nonzeros per staging buffer of the host-buffer entry points below (default 2^24; two buffers of
+ * 8 (d + 1) bytes per nonzero each).  Inputs longer than this are streamed in chunks. */
+int ttsk_set_stage_nnz(ttsk_ctx *ctx, int64_t nnz);
 int ttsk_trim(ttsk_ctx *ctx);
 /* Milliseconds spent in the sketch kernels of the most recent ttsk_sparse_sketch* call,
  * measured with CUDA events on the launching stream (synchronises). */

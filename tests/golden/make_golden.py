@@ -195,10 +195,59 @@ def gen_ttdrm_cores():
     print("ttdrm_cores.npz")
 
 
+def gen_stt_ops():
+    """SketchedTensorTrain streaming operations (sketch.py:272-361 of the reference): `+` (sketch update with
+    the stored DRMs), `increase_rank` (block (0, 0) reused), `.T`, `to_tt`."""
+    store = {}
+    shape = (7, 8, 9, 10)
+    sp = make_sparse(shape, 300, 1)
+    sp_b = make_sparse(shape, 150, 9)
+    tt_b = TensorTrain.random(shape, (2, 3, 2), seed=10)
+    lrank, rrank = (3, 4, 5), (5, 6, 7)
+    tensor_pack("a_T", sp, store)
+    tensor_pack("b_T", sp_b, store)
+    tensor_pack("c_T", tt_b, store)
+    # ---- SparseGaussianDRM: add, increase_rank, transpose
+    left = SparseGaussianDRM(lrank, shape=shape, transpose=False, seed=11)
+    right = SparseGaussianDRM(rrank, shape=shape, transpose=True, seed=23)
+    stt = stream_sketch(sp, lrank, rrank, left_drm=left, right_drm=right)
+    added = stt + sp_b
+    sketch_pack("gauss_add", added.Psi_cores, added.Omega_mats, store)
+    new_l, new_r = (4, 6, 6), (6, 8, 9)
+    inc = stt.increase_rank(sp, new_l, new_r)
+    sketch_pack("gauss_inc", inc.Psi_cores, inc.Omega_mats, store)
+    store["gauss_inc_lrank"] = np.array(new_l, dtype=np.int64)
+    store["gauss_inc_rrank"] = np.array(new_r, dtype=np.int64)
+    tr = stt.T
+    sketch_pack("gauss_T", tr.Psi_cores, tr.Omega_mats, store)
+    for i, c in enumerate(tr.C_cores()):
+        store[f"gauss_T_C{i}"] = c
+    for i, c in enumerate(inc.to_tt().cores):
+        store[f"gauss_inc_C{i}"] = c
+    # ---- TensorTrainDRM: add a TensorTrain to the sketch of a sparse tensor
+    left = TensorTrainDRM(lrank, shape=shape, transpose=False, seed=11)
+    right = TensorTrainDRM(rrank, shape=shape, transpose=True, seed=23)
+    drm_pack("tt_L", left, store)
+    drm_pack("tt_R", right, store)
+    stt = stream_sketch(sp, lrank, rrank, left_drm=left, right_drm=right)
+    added = stt + tt_b
+    sketch_pack("tt_add", added.Psi_cores, added.Omega_mats, store)
+    for i, c in enumerate(added.to_tt().cores):
+        store[f"tt_add_C{i}"] = c
+    store["lrank"] = np.array(lrank, dtype=np.int64)
+    store["rrank"] = np.array(rrank, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "stt_ops.npz"), **store)
+    print("stt_ops.npz")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "stt_ops":  # later additions leave the earlier fixtures untouched
+        gen_stt_ops()
+        sys.exit(0)
     gen_lazy_gaussian()
     gen_sketches()
     gen_ttdrm_cores()
+    gen_stt_ops()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")

@@ -36,6 +36,8 @@ def _oracle_local_sketch(part, left_drm, right_drm, total):
             return ("cp", t.cores)
         if isinstance(t, TensorSum):
             return ("sum", [desc(x) for x in t.tensors])
+        if type(t).__name__ == "DenseTensor":
+            return ("dense", t.data)
         raise TypeError(type(t))
 
     def odrm(d):
@@ -44,6 +46,74 @@ def _oracle_local_sketch(part, left_drm, right_drm, total):
 
     Psi, Om = orc.general_sketch(desc(part), odrm(left_drm), odrm(right_drm), "streaming", fast_sparse=True)
     return SketchContainer(Psi, Om).pack()
+
+
+def _desc(t):
+    from tt_sketch.tensor import CPTensor, SparseTensor, TensorSum, TensorTrain
+
+    if isinstance(t, SparseTensor):
+        return ("sparse", t.shape, np.asarray(t.indices), t.entries)
+    if isinstance(t, TensorTrain):
+        return ("tt", t.cores)
+    if isinstance(t, CPTensor):
+        return ("cp", t.cores)
+    if isinstance(t, TensorSum):
+        return ("sum", [_desc(x) for x in t.tensors])
+    raise TypeError(type(t))
+
+
+def _odrm(d):
+    from oracle import sketch_oracle as orc
+
+    kind = "gauss" if type(d).__name__ == "SparseGaussianDRM" else "tt"
+    return orc.Drm(kind, d.transpose, d.shape, d.bond_rank_min, d.bond_rank_max, d.seed, list(getattr(d, "cores", [])))
+
+
+class _OracleSequentialOps:
+    """Per-rank contributions to the orthogonal sketch through the oracle (test infrastructure only): the
+    same interface as tt_sketch.distributed._GpuSequentialOps."""
+
+    def __init__(self, part, left_drm, right_drm, shape):
+        from oracle import sketch_oracle as orc
+
+        self.orc, self.shape, self.d = orc, tuple(shape), len(shape)
+        self.t = _desc(part) if part is not None else None
+        self.L, self.R = _odrm(left_drm), _odrm(right_drm)
+        self.rL, self.rR = self.L.rank, self.R.rank
+        self.Rc = orc.drm_contractions(self.R, self.t) if self.t is not None else None
+        self.cores = []
+
+    def omegas(self):
+        import torch
+
+        if self.t is None:
+            return [torch.zeros(a, b, dtype=torch.float64) for a, b in zip(self.rL, self.rR)]
+        Lc = self.orc.drm_contractions(self.L, self.t)
+        return [torch.from_numpy(self.orc.omega(self.t, Lc[mu], self.Rc[mu], mu)) for mu in range(self.d - 1)]
+
+    def psi(self, mu, prev_core):
+        import torch
+
+        if prev_core is not None:
+            self.cores.append(np.asarray(prev_core))
+        r1 = self.rL[mu - 1] if mu > 0 else 1
+        r2 = self.rR[mu] if mu < self.d - 1 else 1
+        if self.t is None:
+            return torch.zeros(r1, self.shape[mu], r2, dtype=torch.float64)
+        Lm = None
+        if mu > 0:
+            od = self.orc.Drm("tt", False, self.shape, (0,) * (self.d - 1), tuple(self.rL), cores=list(self.cores))
+            Lm = self.orc.drm_contractions_prefix(od, self.t, mu - 1)
+        Rm = self.Rc[mu] if mu < self.d - 1 else None
+        return torch.from_numpy(self.orc.psi(self.t, Lm, Rm, mu, (r1, self.shape[mu], r2), True))
+
+    def orth(self, P, Omega):
+        import torch
+
+        return torch.from_numpy(self.orc.orth_step(np.asarray(P), np.asarray(Omega)))
+
+    def to_host(self, t):
+        return np.asarray(t)
 
 
 def _worker(rank, world, port, out_dir):
@@ -89,6 +159,29 @@ def _worker(rank, world, port, out_dir):
         # 4. a lone TT does not shard: rank 0 sketches it, the others add zeros
         tt = TensorTrain.random(shape, 2, seed=8)
         assert (shard_tensor(tt, world, rank) is None) == (rank != 0)
+        # 5. dense tensor: slabs along the first mode, DRMs restricted to the slab
+        from tt_sketch.distributed import DenseSlab, distributed_orthogonal_sketch
+        from tt_sketch.tensor import DenseTensor
+
+        dn = DenseTensor(np.random.default_rng(3).standard_normal(shape))
+        slab = shard_tensor(dn, world, rank)
+        assert isinstance(slab, DenseSlab) and (slab.lo, slab.hi) == shard_bounds(shape[0], world, rank)
+        got = distributed_stream_sketch(dn, Lt, Rt, local_sketch=_oracle_local_sketch)
+        want = _oracle_local_sketch(dn, Lt, Rt, got.pack().size)
+        assert np.allclose(got.pack(), want, rtol=1e-11, atol=1e-11)
+        # 6. ranks holding different DRMs are detected before anything is reduced
+        bad = SparseGaussianDRM((5, 6, 7), shape=shape, transpose=True, seed=100 + rank)
+        try:
+            distributed_stream_sketch(sp, L, bad, local_sketch=_oracle_local_sketch)
+            raise AssertionError("DRM mismatch not detected")
+        except ValueError as e:
+            assert "different DRMs" in str(e)
+        # 7. orthogonal sketch of a TensorSum: Omega reduced once, every Psi_mu before its QR
+        cores = distributed_orthogonal_sketch(tsum, Lt, Rt, ops_factory=_OracleSequentialOps)
+        from oracle import sketch_oracle as orc
+        want_cores, _ = orc.general_sketch(_desc(tsum), _odrm(Lt), _odrm(Rt), "orthogonal")
+        for a, b in zip(cores, want_cores):
+            assert a.shape == b.shape and np.allclose(a, b, rtol=1e-9, atol=1e-10)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

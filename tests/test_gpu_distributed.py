@@ -49,6 +49,24 @@ def _worker(rank, world, port, out_dir):
         want = stream_sketch(tsum, (6, 7, 8), (9, 10, 11), left_drm=Lt, right_drm=Rt)
         a, b = got.pack(), want.sketch_.pack()
         assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+        # dense tensor sharded in slabs of the first mode (BASELINE configs[0] shape)
+        from tt_sketch.distributed import distributed_orthogonal_sketch
+        from tt_sketch.sketch import orthogonal_sketch
+        from tt_sketch.tensor import DenseTensor
+
+        shape3 = (20,) * 5
+        dn = DenseTensor(np.random.default_rng(0).standard_normal(shape3))
+        Ld = TensorTrainDRM((10,) * 4, shape=shape3, transpose=False, seed=1)
+        Rd = TensorTrainDRM((15,) * 4, shape=shape3, transpose=True, seed=2)
+        got = distributed_stream_sketch(dn, Ld, Rd)
+        want = stream_sketch(dn, (10,) * 4, (15,) * 4, left_drm=Ld, right_drm=Rd)
+        a, b = got.pack(), want.sketch_.pack()
+        assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+        # orthogonal sketch of a TensorSum: Psi_mu all-reduced before every QR
+        cores = distributed_orthogonal_sketch(tsum, Lt, Rt)
+        want_tt = orthogonal_sketch(tsum, (6, 7, 8), (9, 10, 11), left_drm=Lt, right_drm=Rt)
+        for c, w in zip(cores, want_tt.cores):
+            assert c.shape == w.shape and np.max(np.abs(c - w)) <= 1e-9 * np.max(np.abs(w))
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -115,3 +115,32 @@ def test_sketch_oracle_vs_golden(oracle_lib, name):
             assert rel_err(a, b) < TOL
         for a, b in zip(Om, stored_list(z, name + "_blocked_Omega")):
             assert rel_err(a, b) < TOL
+
+
+def test_oracle_matches_reference_stt_ops_golden():
+    """The oracle reproduces the reference's SketchedTensorTrain `+` and `increase_rank` outputs
+    (tests/golden/stt_ops.npz): a sketch update is the sum of sketches, a rank increase is the blocked sketch
+    over the slices [0, old, new] (reference sketch.py:292-349)."""
+    from _golden import load, rel_err, stored_list, tensor_desc
+    from oracle import sketch_oracle as orc
+
+    z = load("stt_ops.npz")
+    shape = (7, 8, 9, 10)
+    lrank = tuple(int(x) for x in z["lrank"]); rrank = tuple(int(x) for x in z["rrank"])
+    A, B = tensor_desc(z, "a_T"), tensor_desc(z, "b_T")
+    oL = orc.Drm("gauss", False, shape, (0,) * 3, lrank, 11)
+    oR = orc.Drm("gauss", True, shape, (0,) * 3, rrank, 23)
+    Pa, Oa = orc.general_sketch(A, oL, oR, "streaming")
+    Pb, Ob = orc.general_sketch(B, oL, oR, "streaming")
+    for a, b, w in zip(Pa, Pb, stored_list(z, "gauss_add_Psi")):
+        assert rel_err(a + b, w) < 1e-12
+    for a, b, w in zip(Oa, Ob, stored_list(z, "gauss_add_Omega")):
+        assert rel_err(a + b, w) < 1e-12
+    new_l = tuple(int(x) for x in z["gauss_inc_lrank"]); new_r = tuple(int(x) for x in z["gauss_inc_rrank"])
+    oL2 = orc.Drm("gauss", False, shape, (0,) * 3, new_l, 11)
+    oR2 = orc.Drm("gauss", True, shape, (0,) * 3, new_r, 23)
+    P, O = orc.blocked_sketch(A, oL2, oR2, [(0,) * 3, lrank, new_l], [(0,) * 3, rrank, new_r])
+    for a, w in zip(P, stored_list(z, "gauss_inc_Psi")):
+        assert rel_err(a, w) < 1e-12
+    for a, w in zip(O, stored_list(z, "gauss_inc_Omega")):
+        assert rel_err(a, w) < 1e-12

@@ -91,6 +91,7 @@ int ttsk_create(int device, ttsk_ctx** out) {
     if (getenv("TTSK_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(getenv("TTSK_L2_FETCH")));
 #endif
     ttsk_ctx* c = new ttsk_ctx();
+    if (getenv("TTSK_STAGE_NNZ") && atoll(getenv("TTSK_STAGE_NNZ")) > 0) c->stage_nnz = atoll(getenv("TTSK_STAGE_NNZ"));
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     TTSK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -188,6 +189,12 @@ int ttsk_set_table_cache_cap(ttsk_ctx* ctx, int64_t bytes) {
     return TTSK_OK;
 }
 int64_t ttsk_table_cache_bytes(ttsk_ctx* ctx) { return ctx ? ctx->table_bytes : -1; }
+
+int ttsk_set_stage_nnz(ttsk_ctx* ctx, int64_t nnz) {
+    TTSK_ARG(ctx != nullptr && nnz >= 1, "ttsk_set_stage_nnz");
+    ctx->stage_nnz = nnz;
+    return TTSK_OK;
+}
 
 int ttsk_trim(ttsk_ctx* ctx) {
     TTSK_ARG(ctx != nullptr, "ctx is NULL");

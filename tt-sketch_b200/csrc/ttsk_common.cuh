@@ -76,6 +76,7 @@ struct ttsk_ctx {
     std::vector<TableEntry> tables;  // least recently used first
     int64_t table_bytes = 0;
     int64_t table_cap = (int64_t)6 << 30;
+    int64_t stage_nnz = (int64_t)1 << 24;  // nonzeros per staging buffer of the host-buffer entry points
     int64_t plan_gen = 0;  // generation id of the sparse plan being built: its tables are never evicted
 
     int ws_reserve(int64_t bytes);              // make the arena at least this large (may sync)

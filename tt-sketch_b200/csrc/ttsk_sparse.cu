@@ -971,8 +971,7 @@ static int sparse_sketch_from_host(ttsk_ctx* ctx, int d, const int64_t* h_shape,
     const int64_t total = ttsk_sketch_size(d, h_shape, rL, rR);
     // chunk: bounded by the chain workspace and by a staging size that overlaps well
     int64_t chunk = pick_chunk(d, std::max<int64_t>(nnz, 1), left, right, (int64_t)8 << 30);
-    static const int64_t stage_env = getenv("TTSK_STAGE_NNZ") ? atoll(getenv("TTSK_STAGE_NNZ")) : 0;
-    const int64_t stage_cap = stage_env > 0 ? stage_env : (int64_t)1 << 24;  // 16M nonzeros = 640 MB per staging buffer at d=4
+    const int64_t stage_cap = ctx->stage_nnz;  // default 16M nonzeros = 640 MB per staging buffer at d=4
     if (chunk > stage_cap) chunk = stage_cap;
     const int64_t rec = (int64_t)(d + 1) * 8;
     const int64_t stage_bytes = align_up(chunk * rec, 256);

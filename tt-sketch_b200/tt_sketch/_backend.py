@@ -55,6 +55,7 @@ SIGNATURES = {
     "ttsk_sg_pass_count": (c_int64, [c_void_p]),
     "ttsk_set_table_cache_cap": (c_int, [c_void_p, c_int64]),
     "ttsk_table_cache_bytes": (c_int64, [c_void_p]),
+    "ttsk_set_stage_nnz": (c_int, [c_void_p, c_int64]),
     "ttsk_trim": (c_int, [c_void_p]),
     "ttsk_lazy_gaussian": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, POINTER(c_int64), c_int, c_int,
                                    c_uint64, c_void_p, c_void_p]),

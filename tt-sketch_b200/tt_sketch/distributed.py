@@ -10,8 +10,15 @@ tensor.py:215-234 (`SparseTensor.split`):
   * SparseTensor : contiguous nonzero ranges of equal size (`SparseTensor.split` semantics);
   * TensorSum    : summands dealt round-robin (sparse summands are additionally range-split so
                    one huge sparse term does not land on a single rank);
-  * TensorTrain / CPTensor / DenseTensor given alone do not shard usefully (inputs of a few MB,
-    sequential chains): rank 0 sketches them and the others contribute zeros ("replicas only").
+  * DenseTensor   : slabs along the first mode, X[lo:hi]; a rank sketches its slab with the DRMs restricted
+                   to it (`TensorTrainDRM.restrict_first_mode`): rows lo:hi of Psi_0 are its own, every
+                   other Psi / Omega is a partial sum;
+  * TensorTrain / CPTensor given alone do not shard usefully (inputs of a few MB, sequential chains):
+    rank 0 sketches them and the others contribute zeros ("replicas only").
+
+`distributed_orthogonal_sketch` shards a TensorSum the same way for `orthogonal_sketch`: Omega is reduced once,
+and every Psi_mu is all-reduced BEFORE its QR (reference sketch_dispatch.py:251-271 sums the summands' Psi
+before `orth_step`), i.e. d small all-reduces instead of one.
 
 DRMs are seed-defined, so every rank generates identical DRM entries with no communication.
 One process per GPU (`torchrun`), `torch.distributed` with the NCCL backend over NVLink; the
@@ -26,7 +33,17 @@ from typing import Callable, List, Optional
 import numpy as np
 
 from tt_sketch.sketch_container import SketchContainer
-from tt_sketch.tensor import SparseTensor, Tensor, TensorSum
+from tt_sketch.tensor import DenseTensor, SparseTensor, Tensor, TensorSum
+
+
+class DenseSlab:
+    """Rows [lo, hi) of the first mode of a DenseTensor: what one rank sketches."""
+
+    def __init__(self, tensor: DenseTensor, lo: int, hi: int) -> None:
+        self.lo, self.hi = lo, hi
+        self.full_shape = tuple(tensor.shape)
+        self.tensor = DenseTensor(tensor.data[lo:hi])
+        self.shape = self.full_shape
 
 
 def shard_bounds(n: int, world: int, rank: int):
@@ -62,6 +79,9 @@ def shard_tensor(tensor: Tensor, world: int, rank: int) -> Optional[Tensor]:
             if part.nnz > 0:
                 mine.append(part)
         return TensorSum(mine, shape=tensor.shape) if mine else None
+    if isinstance(tensor, DenseTensor):
+        lo, hi = shard_bounds(tensor.shape[0], world, rank)
+        return DenseSlab(tensor, lo, hi) if hi > lo else None
     return tensor if rank == 0 else None
 
 
@@ -85,6 +105,52 @@ def _gpu_local_sketch(part: Optional[Tensor], left_drm, right_drm, total: int):
     return packed
 
 
+def _slab_sketch(slab: DenseSlab, left_drm, right_drm, total: int, local_sketch: Callable):
+    """Packed partial sketch of a dense slab in the layout of the FULL tensor: the slab's Psi_0 block lands in
+    rows lo:hi of Psi_0, every other block is a partial sum (dense_sketch.py:7-52 of the reference is linear in X).
+    `local_sketch` sketches the slab as a tensor of its own with the DRMs restricted to it."""
+    import torch
+
+    for drm in (left_drm, right_drm):
+        if not hasattr(drm, "restrict_first_mode"):
+            raise ValueError(f"DRM {type(drm).__name__} cannot be restricted to a slab of the first mode")
+    n0, rows = slab.full_shape[0], slab.hi - slab.lo
+    r0 = int(right_drm.bond_rank[0])
+    part = local_sketch(slab.tensor, left_drm.restrict_first_mode(slab.lo, slab.hi),
+                        right_drm.restrict_first_mode(slab.lo, slab.hi), total - (n0 - rows) * r0)
+    if not isinstance(part, torch.Tensor):
+        part = torch.from_numpy(np.ascontiguousarray(part, dtype=np.float64))
+    packed = torch.zeros(total, dtype=torch.float64, device=part.device)
+    packed[slab.lo * r0:slab.hi * r0] = part[:rows * r0]
+    packed[n0 * r0:] = part[rows * r0:]
+    return packed
+
+
+def check_same_drms(left_drm, right_drm, group=None) -> None:
+    """Every rank must hold the same DRMs (kind, seed, column ranges): a DRM built with seed=None, or the
+    default right seed of stream_sketch (`hash(str(d))`, randomised per process), differs between ranks and the
+    all-reduce would then silently sum sketches made with different maps."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+
+    def fp(d):
+        cores = getattr(d, "cores", None)
+        core_sum = None
+        if cores is not None and len(cores) and isinstance(cores[0], np.ndarray):
+            core_sum = float(sum(np.asarray(c).ravel()[:: max(1, c.size // 64)].sum() for c in cores))
+        return (type(d).__name__, bool(d.transpose), int(d.seed), tuple(d.rank_min), tuple(d.rank_max),
+                tuple(d.true_rank), tuple(d.shape), core_sum)
+
+    mine = (fp(left_drm) if left_drm is not None else None, fp(right_drm))
+    everyone = [None] * dist.get_world_size(group)
+    dist.all_gather_object(everyone, mine, group=group)
+    if any(e != everyone[0] for e in everyone):
+        raise ValueError("ranks hold different DRMs (pass explicit DRMs with explicit seeds to every rank): "
+                         f"{everyone}")
+
+
 def distributed_stream_sketch(tensor: Tensor, left_drm, right_drm, group=None,
                               local_sketch: Optional[Callable] = None) -> SketchContainer:
     """Streaming sketch of `tensor` computed by all ranks of `group`; every rank returns the
@@ -98,8 +164,12 @@ def distributed_stream_sketch(tensor: Tensor, left_drm, right_drm, group=None,
     shape = tuple(tensor.shape)
     rL, rR = tuple(left_drm.bond_rank), tuple(right_drm.bond_rank)
     _, total = SketchContainer.layout(shape, rL, rR)
+    check_same_drms(left_drm, right_drm, group)
     part = shard_tensor(tensor, world, rank)
-    packed = (local_sketch or _gpu_local_sketch)(part, left_drm, right_drm, total)
+    if isinstance(part, DenseSlab):
+        packed = _slab_sketch(part, left_drm, right_drm, total, local_sketch or _gpu_local_sketch)
+    else:
+        packed = (local_sketch or _gpu_local_sketch)(part, left_drm, right_drm, total)
     if not isinstance(packed, torch.Tensor):
         packed = torch.from_numpy(np.ascontiguousarray(packed, dtype=np.float64))
     if packed.numel() != total:
@@ -130,3 +200,97 @@ def distributed_blocked_stream_sketch(tensor: Tensor, left_drm, right_drm, left_
             blocks[(i, j)] = distributed_stream_sketch(tensor, left_drm.slice(a, b), right_drm.slice(c, d), group,
                                                        local_sketch)
     return _assemble_blocked_stream_sketches(left_rank_slices, right_rank_slices, tensor.shape, blocks)
+
+
+# ------------------------------------------------------------------ orthogonal sketch of a TensorSum
+class _GpuSequentialOps:
+    """This rank's contributions to the orthogonal sketch, on its GPU (see sketch_dispatch._sequential_sketch)."""
+
+    def __init__(self, part: Optional[Tensor], left_drm, right_drm, shape):
+        from tt_sketch import _backend as be
+        from tt_sketch.sketch_dispatch import (OMEGA_DEVICE, PSI_DEVICE, OrthogTTDRM, _check_supported, _summands,
+                                               get_sketch_method)
+
+        self.be, self.shape, self.d = be, tuple(shape), len(shape)
+        self.parts = _summands(part) if part is not None else []
+        self.rL, self.rR = tuple(left_drm.bond_rank), tuple(right_drm.bond_rank)
+        self.om, self.ps = OMEGA_DEVICE, PSI_DEVICE
+        for X in self.parts:
+            _check_supported(X, left_drm)
+            _check_supported(X, right_drm)
+        self.Rc = [list(get_sketch_method(X, right_drm, device=True)(X)) for X in self.parts]
+        self.Lc = [list(get_sketch_method(X, left_drm, device=True)(X)) for X in self.parts]
+        self.left_psi = OrthogTTDRM(self.rL, TensorSum(self.parts, shape=self.shape)) if self.parts else None
+
+    def omegas(self):
+        out = []
+        for mu in range(self.d - 1):
+            o = self.be.zeros((self.rL[mu], self.rR[mu]))
+            for s, X in enumerate(self.parts):
+                self.om[type(X)](self.Lc[s][mu], self.Rc[s][mu], tensor=X, mu=mu, out=o)
+            out.append(o)
+        self.Lc = None
+        return out
+
+    def psi(self, mu: int, prev_core):
+        r1 = self.rL[mu - 1] if mu > 0 else 1
+        r2 = self.rR[mu] if mu < self.d - 1 else 1
+        P = self.be.zeros((r1, self.shape[mu], r2))
+        lefts = [None] * len(self.parts)
+        if mu > 0 and self.parts:
+            self.left_psi.add_core(prev_core)
+            lefts = next(self.left_psi)
+        for s, X in enumerate(self.parts):
+            self.ps[type(X)](lefts[s], self.Rc[s][mu] if mu < self.d - 1 else None, tensor=X, mu=mu, out=P)
+        return P
+
+    def orth(self, P, Omega):
+        from tt_sketch.sketch_dispatch import orth_step_device
+
+        return orth_step_device(P, Omega)
+
+    def to_host(self, t):
+        return self.be.to_host(t)
+
+
+def distributed_orthogonal_sketch(tensor: Tensor, left_drm, right_drm, group=None, ops_factory=None):
+    """`orthogonal_sketch` (reference sketch.py:81-151 -> general_sketch method="orthogonal") of a TensorSum /
+    SparseTensor with the summands and nonzeros spread over the ranks of `group`.  Returns the list of
+    orthogonalised TT cores (host arrays), identical on every rank.  `ops_factory(part, left, right, shape)`
+    supplies the per-rank contractions (default: this rank's GPU)."""
+    import torch
+    import torch.distributed as dist
+
+    on = dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
+    shape = tuple(tensor.shape)
+    d = len(shape)
+    check_same_drms(left_drm, right_drm, group)
+    part = shard_tensor(tensor, world, rank)
+    if isinstance(part, DenseSlab):
+        raise ValueError("distributed_orthogonal_sketch shards TensorSum / SparseTensor inputs")
+    ops = (ops_factory or _GpuSequentialOps)(part, left_drm, right_drm, shape)
+
+    def reduce(ts):
+        if world == 1:
+            return ts
+        flat = torch.cat([torch.as_tensor(t).reshape(-1) for t in ts])  # one all-reduce for the whole list
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        out, off = [], 0
+        for t in ts:
+            n = int(np.prod(t.shape))
+            out.append(flat[off:off + n].reshape(t.shape))
+            off += n
+        return out
+
+    Omega = reduce(ops.omegas())
+    cores = []
+    prev = None
+    for mu in range(d):
+        P = reduce([ops.psi(mu, prev)])[0]
+        if mu < d - 1:
+            P = ops.orth(P, Omega[mu])
+        prev = P
+        cores.append(P)
+    return [np.asarray(ops.to_host(c)) for c in cores]

@@ -38,15 +38,29 @@ class TensorTrainDRM(CansketchSparse, CansketchTT, CansketchCP, CanSlice, Canske
         # a slice shares the parent's cores (the reference regenerates identical ones)
         return {"cores": self.cores, "_dev_cores": self._dev_cores}
 
+    def restrict_first_mode(self, lo: int, hi: int) -> "TensorTrainDRM":
+        """The same DRM for the slab X[lo:hi] of a tensor (multi-GPU slab sharding): a left DRM keeps rows
+        lo:hi of its first core; a right DRM's cores never touch the first mode (its TT is built for the
+        reversed shape and drops that mode's core, reference tensor_train_drm.py:46-56), so only `shape` changes."""
+        cores = list(self.cores)
+        if not self.transpose:
+            c0 = cores[0]
+            cores[0] = c0[:, lo:hi, :].contiguous() if be.is_device(c0) else np.ascontiguousarray(c0[:, lo:hi, :])
+        return type(self)(rank=self.bond_rank_max, shape=(hi - lo,) + tuple(self.shape[1:]), transpose=self.transpose,
+                          seed=self.seed, rank_min=self.bond_rank_min, rank_max=self.bond_rank_max,
+                          true_rank=self.bond_true_rank, cores=cores)
+
     def device_core(self, k: int):
         """Core k (DRM orientation) as a contiguous device tensor, uploaded once."""
         c = self.cores[k]
         if be.is_device(c):
             return c if c.is_contiguous() else c.contiguous()
-        key = id(c)
-        if key not in self._dev_cores:
-            self._dev_cores[key] = be.to_device(c, np.float64)
-        return self._dev_cores[key]
+        key = (be.device_index(), id(c))
+        hit = self._dev_cores.get(key)
+        if hit is None or hit[0] is not c:  # the host array is kept alive next to its upload, so ids cannot be recycled
+            hit = (c, be.to_device(c, np.float64))
+            self._dev_cores[key] = hit
+        return hit[1]
 
     # ------------------------------------------------------------------ sparse
     @handle_transpose
