@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- stream_sketch throughput of the B200 sketching path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--nnz NNZ] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--nnz NNZ] [--impl reference] [--config C1|C2|C3|C4|C5]
 
 Workload (BASELINE.json configs[3], SURVEY.md section 8d "C4"): one step = one streaming sketch
 (all d Psi cores + d-1 Omega matrices) of a synthetic order-4 COO tensor, shape
@@ -13,8 +13,14 @@ Multi-GPU (torchrun, one rank per GPU): the SAME 1e8 nonzeros are sharded into e
 ranges (strong scaling), every rank sketches its shard, one NCCL all-reduce of the packed
 sketch (16.4 M doubles) combines them inside the timed region.
 
-`--impl reference` times the CPU restatement of the reference algorithm (oracle/, incl. its
-O(n_mu * nnz) mask loop) on a bounded sample of the same workload on the host cores.
+`--impl reference` times THE REFERENCE ITSELF (the unmodified package that oracle/build_ref.sh installs
+under oracle/_ref/, git-ignored) on a bounded sample of the same workload on the host cores
+(`cpu_baseline.kind` = "reference"); the same run, in a subprocess, is the `cpu_baseline` of the GPU arm.
+
+`--config` selects another BASELINE.json configuration (default C4, the one the metric is quoted on):
+C1 dense 20^5 stream_sketch, C2 TT orthogonal_sketch, C3 CP stream_sketch (all three at full size, one GPU
+each: they do not shard -- N ranks run N replicas), C5 TensorSum(100 TT + sparse) blocked_stream_sketch with
+TensorTrainDRMs (1.25e8 nonzeros PER GPU: weak scaling, 1e9 at 8 GPUs).  See bench_configs.py.
 """
 import argparse
 import json
@@ -138,20 +144,23 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_rate(nnz_sample, repeats=1):
-    """The reference algorithm (oracle port: hash->ndtri rows materialised per bond, Omega GEMM,
-    Psi by the O(n_mu*nnz) boolean-mask loop of sparse_sketch.py:49-69) on the host."""
-    from oracle import sketch_oracle as orc
+def reference_sketch_seconds(nnz_sample):
+    """One stream_sketch of the first `nnz_sample` nonzeros of the workload by THE REFERENCE (oracle/_ref/pkg:
+    unmodified tt_sketch package + its Cython generator), same shape / DRM kinds / ranks / seeds."""
+    from oracle.ref_import import import_reference
+
+    import_reference()
+    from tt_sketch.drm import SparseGaussianDRM as RefGauss
+    from tt_sketch.sketch import stream_sketch as ref_stream_sketch
+    from tt_sketch.tensor import SparseTensor as RefSparse
 
     idx, val = make_coo(nnz_sample, 0, nnz_sample)
-    oL = orc.Drm("gauss", False, SHAPE, (0,) * 3, RL, SEED_L)
-    oR = orc.Drm("gauss", True, SHAPE, (0,) * 3, RR, SEED_R)
-    best = float("inf")
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        orc.general_sketch(("sparse", SHAPE, idx, val), oL, oR, "streaming")
-        best = min(best, time.perf_counter() - t0)
-    return nnz_sample / best, best
+    X = RefSparse(SHAPE, idx, val)
+    left = RefGauss(RL, shape=SHAPE, transpose=False, seed=SEED_L)
+    right = RefGauss(RR, shape=SHAPE, transpose=True, seed=SEED_R)
+    t0 = time.perf_counter()
+    ref_stream_sketch(X, RL, RR, left_drm=left, right_drm=right)
+    return time.perf_counter() - t0
 
 
 def blas_threads():
@@ -163,34 +172,54 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def reference_sample_note(sample, cores):
+    return (f"first {sample} nonzeros of the workload per step (the reference cannot run nnz=1e8: >=144 GB of "
+            f"(r x nnz) intermediates, ~5.7 h, int overflow at fast_lazy_gaussian.pyx:95; it is linear in nnz); "
+            f"the unmodified reference package from oracle/_ref (NumPy + its Cython generator); BLAS threads={cores}, "
+            f"generator and mask loop single-threaded by construction")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
     sample = args.ref_nnz
     times = []
     for i in range(args.warmup + args.steps):
-        rate, sec = cpu_reference_rate(sample)
+        sec = reference_sketch_seconds(sample)
         if i >= args.warmup:
             times.append(sec)
     sec = float(np.mean(times))
     value = sample / sec
     cores = blas_threads()
+    cfg = config_dict(args.nnz, args.gpus)
+    cfg["workload"] += f"; THIS ARM times a {sample}-nonzero sample of it per step"
+    cfg["sample_nnz"] = int(sample)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args.nnz, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"first {sample} nonzeros of the workload per step (the reference cannot run "
-                                   f"nnz=1e8: >=144 GB of (r x nnz) intermediates, ~5.7 h); NumPy oracle port of the "
-                                   f"reference algorithm incl. its O(n_mu*nnz) mask loop; BLAS threads={cores}, the "
-                                   f"generator and mask loop are single-threaded like the reference"},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": reference_sample_note(sample, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+def cpu_baseline_subprocess(extra_args, timeout=900):
+    """The reference arm in a subprocess (the reference's package is also called tt_sketch, so it cannot share
+    a process with the product); returns its parsed JSON line."""
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"] + extra_args
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    if p.returncode != 0 or not lines:
+        raise RuntimeError("reference arm failed: " + p.stderr[-2000:])
+    return json.loads(lines[-1])
 
 
 def config_dict(nnz, gpus):
@@ -210,12 +239,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--nnz", type=float, default=1e8)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--ref-nnz", type=int, default=20000, help="sample size of one --impl reference step")
-    ap.add_argument("--cpu-nnz", type=int, default=50000, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--ref-nnz", type=int, default=100000, help="nonzeros of one --impl reference step (BASELINE.md section 3)")
+    ap.add_argument("--cpu-nnz", type=int, default=50000, help="nonzeros of the cpu_baseline leg of the GPU arm")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
     args = ap.parse_args()
     args.nnz = int(args.nnz)
+    if args.config != "C4":
+        import bench_configs
+
+        return bench_configs.main(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -372,14 +406,8 @@ def main():
             "checksum": checksum,
         }
         if world == 1 and not args.no_cpu:
-            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
-            rate, sec = cpu_reference_rate(args.cpu_nnz)
-            cores = blas_threads()
-            out["cpu_baseline"] = {
-                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"first {args.cpu_nnz} nonzeros of the same workload, one run of {sec:.1f} s; NumPy oracle port "
-                          f"of the reference algorithm (mask loop O(n_mu*nnz)); BLAS threads={cores}, generator and "
-                          f"mask loop single-threaded like the reference"}
+            ref = cpu_baseline_subprocess(["--ref-nnz", str(args.cpu_nnz)])
+            out["cpu_baseline"] = dict(ref["cpu_baseline"], ms=ref["ms_per_step"])
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -27,3 +27,14 @@ gcc -O2 -fPIC -shared -fopenmp -fwrapv -fno-strict-aliasing \
     -I"$NPINC" -I"$PYINC" "$OUT/fast_lazy_gaussian.c" -o "$OUT/fast_lazy_gaussian$SUFFIX"
 rm -f "$OUT/fast_lazy_gaussian.c"
 echo "build_ref: built $OUT/fast_lazy_gaussian$SUFFIX"
+# The reference itself is pure Python around that one extension: install the package (an unmodified copy of
+# its tt_sketch/ directory, like `pip install --target`) next to it so that bench.py --impl reference and the
+# cpu_baseline leg can time THE REFERENCE on the GPU box's host cores.  oracle/_ref/ is git-ignored build
+# output (it travels with gpurun); nothing of it enters the repository.
+PKG="$OUT/pkg"
+rm -rf "$PKG"
+mkdir -p "$PKG"
+cp -r "$REF/tt_sketch" "$PKG/tt_sketch"
+find "$PKG" -name "__pycache__" -type d -exec rm -rf {} + 2>/dev/null || true
+cp "$OUT/fast_lazy_gaussian$SUFFIX" "$PKG/tt_sketch/drm/"
+echo "build_ref: installed the reference package under $PKG"

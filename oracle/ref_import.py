@@ -1,7 +1,8 @@
 """Import the UNMODIFIED reference package from /root/reference in this container.
 
-TEST INFRASTRUCTURE ONLY (used by tests/golden/make_golden.py and tests that pin the
-oracle when /root/reference is mounted).  Nothing here is importable on the GPU box.
+TEST INFRASTRUCTURE ONLY (used by tests/golden/make_golden.py, tests that pin the oracle, and
+bench.py's reference arm / cpu_baseline leg).  On the GPU box /root/reference does not exist; the
+unmodified copy that oracle/build_ref.sh installed under oracle/_ref/pkg/ is imported instead.
 
 Two runtime workarounds, neither touching reference files:
   1. the Cython extension is loaded from oracle/_ref/ (built by oracle/build_ref.sh) and
@@ -18,8 +19,11 @@ import sys
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("TTSK_REFERENCE", "/root/reference")
 _REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+# /root/reference in the authoring container; on the GPU box the unmodified copy build_ref.sh installed
+REFERENCE_ROOT = os.environ.get("TTSK_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "tt_sketch")):
+    REFERENCE_ROOT = os.path.join(_REF_DIR, "pkg")
 
 
 def reference_available() -> bool:

@@ -194,12 +194,52 @@ def distributed_blocked_stream_sketch(tensor: Tensor, left_drm, right_drm, left_
     for drm in (left_drm, right_drm):
         if not isinstance(drm, CanSlice):
             raise ValueError(f"Blocked sketch not supported for DRM {type(drm).__name__}")
+    from tt_sketch.sketch import merged_block_drms
+
+    merged = merged_block_drms(left_drm, right_drm, left_rank_slices, right_rank_slices)
+    if merged is not None:  # one pass over the shard for all blocks (see merged_block_drms)
+        return distributed_stream_sketch(tensor, merged[0], merged[1], group, local_sketch)
     blocks = {}
     for i, (a, b) in enumerate(zip(left_rank_slices[:-1], left_rank_slices[1:])):
         for j, (c, d) in enumerate(zip(right_rank_slices[:-1], right_rank_slices[1:])):
             blocks[(i, j)] = distributed_stream_sketch(tensor, left_drm.slice(a, b), right_drm.slice(c, d), group,
                                                        local_sketch)
     return _assemble_blocked_stream_sketches(left_rank_slices, right_rank_slices, tensor.shape, blocks)
+
+
+def allreduce_blocked_stream_sketch(local_tensor: Tensor, left_drm, right_drm, left_rank_slices, right_rank_slices,
+                                    group=None, dst: Optional[int] = None) -> Optional[SketchContainer]:
+    """blocked_stream_sketch when every rank ALREADY holds its part of the data (its sparse shard, its share of
+    the summands -- BASELINE configs[4]): local sketch on this rank's GPU, one NCCL reduction of the packed
+    buffer.  With `dst` given only that rank receives (and copies to the host) the result; others return None."""
+    import torch.distributed as dist
+
+    from tt_sketch import _backend as be
+    from tt_sketch.sketch import _assemble_blocked_stream_sketches, merged_block_drms
+    from tt_sketch.sketch_dispatch import streaming_sketch_device
+
+    on = dist.is_initialized() and dist.get_world_size(group) > 1
+    check_same_drms(left_drm, right_drm, group)
+    merged = merged_block_drms(left_drm, right_drm, left_rank_slices, right_rank_slices)
+    pairs = [((0, 0), merged)] if merged is not None else [
+        ((i, j), (left_drm.slice(a, b), right_drm.slice(c, d)))
+        for i, (a, b) in enumerate(zip(left_rank_slices[:-1], left_rank_slices[1:]))
+        for j, (c, d) in enumerate(zip(right_rank_slices[:-1], right_rank_slices[1:]))]
+    blocks = {}
+    for key, (lb, rb) in pairs:
+        packed, (shape, rL, rR) = streaming_sketch_device(local_tensor, lb, rb)
+        if on:
+            if dst is None:
+                dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+            else:
+                dist.reduce(packed, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        if dst is None or not on or dist.get_rank(group) == dst:
+            blocks[key] = SketchContainer.unpack(be.to_host_pinned(packed), shape, rL, rR, copy=False)
+    if not blocks:
+        return None
+    if merged is not None:
+        return blocks[(0, 0)]
+    return _assemble_blocked_stream_sketches(left_rank_slices, right_rank_slices, local_tensor.shape, blocks)
 
 
 # ------------------------------------------------------------------ orthogonal sketch of a TensorSum

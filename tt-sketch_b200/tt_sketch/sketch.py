@@ -248,5 +248,33 @@ def blocked_stream_sketch(tensor: Tensor, left_drm: CanSlice, right_drm: CanSlic
     for drm in (left_drm, right_drm):
         if not isinstance(drm, CanSlice):
             raise ValueError(f"Blocked sketch not supported for DRM {type(drm).__name__}")
+    merged = merged_block_drms(left_drm, right_drm, left_rank_slices, right_rank_slices)
+    if merged is not None:
+        return general_sketch(tensor, merged[0], merged[1], method=SketchMethod.streaming)
     blocks = _blocked_stream_sketch_components(tensor, left_drm, right_drm, left_rank_slices, right_rank_slices)
     return _assemble_blocked_stream_sketches(left_rank_slices, right_rank_slices, tensor.shape, blocks)
+
+
+def merged_block_drms(left_drm: CanSlice, right_drm: CanSlice, left_rank_slices, right_rank_slices):
+    """Block (i, j) of a blocked sketch is the streaming sketch under the column slices
+    [l_i, l_{i+1}) x [r_j, r_{j+1}) of the DRMs, pasted into those rows / columns (reference sketch.py:364-397,
+    446-473), so the assembled result IS the streaming sketch under the slices [l_0, l_last) x [r_0, r_last).
+    For the library's own DRMs -- whose slices are column ranges of one fixed map: a TensorTrainDRM slice
+    recomputes the whole chain and keeps some columns (reference tensor_train_drm.py:60-69), which is why the
+    reference pays blocks x full cost -- the chain is therefore computed ONCE and every block's columns come from
+    it.  Returns the two merged DRMs, or None when the per-block path must run (third-party DRM classes, slices
+    that are not consecutive, merged rank above the fused kernels' 64)."""
+    from tt_sketch.drm import SparseGaussianDRM, TensorTrainDRM
+
+    if type(left_drm) not in (SparseGaussianDRM, TensorTrainDRM) or type(right_drm) not in (SparseGaussianDRM, TensorTrainDRM):
+        return None
+    ls, rs = [tuple(x) for x in left_rank_slices], [tuple(x) for x in right_rank_slices]
+    if len(ls) < 2 or len(rs) < 2:
+        return None
+    for sl in (ls, rs):
+        for a, b in zip(sl[:-1], sl[1:]):
+            if any(y < x for x, y in zip(a, b)):
+                return None
+    if max(max(y - x for x, y in zip(ls[0], ls[-1])), max(y - x for x, y in zip(rs[0], rs[-1]))) > 64:
+        return None
+    return left_drm.slice(ls[0], ls[-1]), right_drm.slice(rs[0], rs[-1])
