@@ -11,10 +11,10 @@ __device__ __forceinline__ double central_nodiv(double b) {
     const double y = __dadd_rn(b, -1.5);
     const double y2 = __dmul_rn(y, y);
     double p = c_nd[0];
-    TTSK_H(p, y2, c_nd[1]); TTSK_H(p, y2, c_nd[2]); TTSK_H(p, y2, c_nd[3]); TTSK_H(p, y2, c_nd[4]);
+    TTSK_HORNER(p, y2, c_nd[1]); TTSK_HORNER(p, y2, c_nd[2]); TTSK_HORNER(p, y2, c_nd[3]); TTSK_HORNER(p, y2, c_nd[4]);
     double q = __dadd_rn(y2, c_nd[5]);
-    TTSK_H(q, y2, c_nd[6]); TTSK_H(q, y2, c_nd[7]); TTSK_H(q, y2, c_nd[8]); TTSK_H(q, y2, c_nd[9]);
-    TTSK_H(q, y2, c_nd[10]); TTSK_H(q, y2, c_nd[11]); TTSK_H(q, y2, c_nd[12]);
+    TTSK_HORNER(q, y2, c_nd[6]); TTSK_HORNER(q, y2, c_nd[7]); TTSK_HORNER(q, y2, c_nd[8]); TTSK_HORNER(q, y2, c_nd[9]);
+    TTSK_HORNER(q, y2, c_nd[10]); TTSK_HORNER(q, y2, c_nd[11]); TTSK_HORNER(q, y2, c_nd[12]);
     const double t = __dmul_rn(__dmul_rn(y2, p), q);
     return __dmul_rn(__dadd_rn(y, __dmul_rn(y, t)), c_misc[0]);
 }
@@ -98,10 +98,10 @@ __device__ __forceinline__ double central_regs(double b, const double (&k)[15]) 
     const double y = __dadd_rn(b, -1.5);
     const double y2 = __dmul_rn(y, y);
     double p = k[0];
-    TTSK_H(p, y2, k[1]); TTSK_H(p, y2, k[2]); TTSK_H(p, y2, k[3]); TTSK_H(p, y2, k[4]);
+    TTSK_HORNER(p, y2, k[1]); TTSK_HORNER(p, y2, k[2]); TTSK_HORNER(p, y2, k[3]); TTSK_HORNER(p, y2, k[4]);
     double q = __dadd_rn(y2, k[5]);
-    TTSK_H(q, y2, k[6]); TTSK_H(q, y2, k[7]); TTSK_H(q, y2, k[8]); TTSK_H(q, y2, k[9]);
-    TTSK_H(q, y2, k[10]); TTSK_H(q, y2, k[11]); TTSK_H(q, y2, k[12]);
+    TTSK_HORNER(q, y2, k[6]); TTSK_HORNER(q, y2, k[7]); TTSK_HORNER(q, y2, k[8]); TTSK_HORNER(q, y2, k[9]);
+    TTSK_HORNER(q, y2, k[10]); TTSK_HORNER(q, y2, k[11]); TTSK_HORNER(q, y2, k[12]);
     const double t = div_rn_safe(__dmul_rn(y2, p), q);
     return __dmul_rn(__dadd_rn(y, __dmul_rn(y, t)), k[13]);
 }

@@ -87,9 +87,8 @@ int ttsk_create(int device, ttsk_ctx** out) {
         ttsk::set_error("device %d is sm_%d%d; libttsk is built for sm_100a only", device, prop.major, prop.minor);
         return TTSK_E_NODEVICE;
     }
-#ifdef TTSK_PROFILE
+    // cache-policy knob (does not change results): bytes the L2 fetches from DRAM around a missing sector
     if (getenv("TTSK_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(getenv("TTSK_L2_FETCH")));
-#endif
     ttsk_ctx* c = new ttsk_ctx();
     if (getenv("TTSK_STAGE_NNZ") && atoll(getenv("TTSK_STAGE_NNZ")) > 0) c->stage_nnz = atoll(getenv("TTSK_STAGE_NNZ"));
     c->device = device;

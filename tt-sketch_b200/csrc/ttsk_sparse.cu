@@ -667,14 +667,18 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
         };
         if (mu == d - 1 && !has_x) {  // last mode: no bucketing needed when the mode fits shared memory
             TTSK_TRY(mark(0));
-            TTSK_TRY(launch_last_mode_unbucketed(ctx, P, st, &flat_done));
+            TTSK_TRY(try_launch_gw_flat(ctx, P, st, &flat_done));
+            if (!flat_done) TTSK_TRY(launch_last_mode_unbucketed(ctx, P, st, &flat_done));
             if (flat_done) { TTSK_TRY(mark(1)); continue; }
         }
         TTSK_TRY(sort_keys(ctx, nnz, idx_rows[mu], shape[mu], sb, st, mu));
         P.keyid = sb.keyid;
         P.offs = sb.offs;
         TTSK_TRY(mark(0));
-        TTSK_TRY(launch_pass(ctx, P, has_x, st));
+        bool gw_done = false;  // warp-autonomous forms (ttsk_sparse_gen.cu) when exactly one source is generated
+        if (!has_x) TTSK_TRY(try_launch_gw_direct(ctx, P, st, &gw_done));
+        if (!gw_done) TTSK_TRY(try_launch_gw_seg(ctx, P, has_x, st, &gw_done));
+        if (!gw_done) TTSK_TRY(launch_pass(ctx, P, has_x, st));
         TTSK_TRY(mark(1));
     }
     return TTSK_OK;
