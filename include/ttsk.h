@@ -180,6 +180,19 @@ int ttsk_tt_sketch(ttsk_ctx *ctx, int d, const int64_t *h_shape, const int32_t *
                    const double *const *h_core_ptrs, const ttsk_drm *left, const ttsk_drm *right,
                    double *d_out, void *stream);
 
+/* ---------------------------------------------------------------- DenseTensor input
+ * Streaming sketch of ONE DenseTensor (d_X: C-order, prod(h_shape) doubles on the device) with TensorTrainDRMs,
+ * ADDED to the packed sketch d_out (layout of ttsk_sparse_sketch).  Replaces, for DenseTensor input and
+ * method=streaming,
+ *   TensorTrainDRM.sketch_dense           tt_sketch/drm/tensor_train_drm.py:109-122
+ *   sketch_omega_dense / sketch_psi_dense  tt_sketch/sketching_methods/dense_sketch.py:7-52
+ * X is read from HBM once (TMA-staged fused first pass: XL_0 = G_0^T X_(0) and Psi_0), the left DRM is swept
+ * through ever smaller partial contractions and every Omega_mu / Psi_mu is a small product with a right-DRM
+ * unfolding used as a flat array like the reference does (its reversed-mode column order included).  Like the
+ * reference the dense sketch ignores rank slices: both DRMs must span their whole cores. */
+int ttsk_dense_sketch(ttsk_ctx *ctx, int d, const int64_t *h_shape, const double *d_X, const ttsk_drm *left,
+                      const ttsk_drm *right, double *d_out, void *stream);
+
 /* ---------------------------------------------------------------- dense building blocks
  * C[b] (M,N) = alpha * A[b] (M,K) @ B[b] (K,N) + beta * C[b], arbitrary element strides
  * (row stride, column stride) so transposes/slices are views.  Backs the TT / CP / dense

@@ -65,14 +65,9 @@ __device__ __forceinline__ double2 ld_shared_v2f64(unsigned addr) {
     return v;
 }
 
-// IL columns of the warp's 32 rows: hash -> uniform -> central branch -> store; tails keep b = 1 + u in the slot and are
-// queued (slot address >> 3).  `salt_addr` -> the columns' salts (u64, warp-uniform), `slot0` -> this lane's slot of
-// the first column.
+// hash -> b = 1 + u (two words) of IL columns of the lane's row; `salt_addr` -> the columns' salts (u64, warp-uniform)
 template <int IL>
-__device__ __forceinline__ void gw_group(unsigned long long flat, unsigned salt_addr, unsigned slot0, unsigned& wq_top,
-                                         unsigned lt) {
-    unsigned hi[IL], lo[IL];
-    double cc[IL];
+__device__ __forceinline__ void gw_hash(unsigned long long flat, unsigned salt_addr, unsigned (&hi)[IL], unsigned (&lo)[IL]) {
     if constexpr (IL % 2 == 0) {
 #pragma unroll
         for (int c = 0; c < IL; c += 2) {
@@ -85,55 +80,120 @@ __device__ __forceinline__ void gw_group(unsigned long long flat, unsigned salt_
 #pragma unroll
         for (int c = 0; c < IL; c++) hash_to_b(flat + ld_shared_u64(salt_addr + 8u * c), hi[c], lo[c]);
     }
+}
+
+// central branch of IL columns -> store; tails keep b = 1 + u in the slot and are queued (slot address >> 3).
+// `slot0` -> this lane's slot of the first column.  One predicate per variate drives the select, the ballot and the
+// queue push (written in PTX: the compiler otherwise materialises the predicate twice).
+template <int IL>
+__device__ __forceinline__ void gw_central(const unsigned (&hi)[IL], const unsigned (&lo)[IL], double (&cc)[IL]) {
 #pragma unroll
     for (int c = 0; c < IL; c++) cc[c] = ndtri_central_b(__hiloint2double((int)(hi[c] | 0x3FF00000u), (int)lo[c]));
+}
+template <int IL>
+__device__ __forceinline__ void gw_store(const unsigned (&hi)[IL], const unsigned (&lo)[IL], const double (&cc)[IL], unsigned slot0,
+                                         unsigned& wq_top, unsigned lt) {
+    const unsigned e0 = slot0 >> 3;
 #pragma unroll
     for (int c = 0; c < IL; c++) {
-        const bool tail = hi[c] - kCentralLo >= kCentralSpan;
-        const unsigned slot = slot0 + (unsigned)(kGwPB * 8 * c);
-        const double b = __hiloint2double((int)(hi[c] | 0x3FF00000u), (int)lo[c]);
-        st_shared_f64(slot, tail ? b : cc[c]);
-        const unsigned m = __ballot_sync(0xffffffffu, tail);
-        if (tail) st_shared_u16(wq_top + 2 * __popc(m & lt), (unsigned short)(slot >> 3));
-        wq_top += 2 * __popc(m);
+        const unsigned bh = hi[c] | 0x3FF00000u;  // high word of b; the tail test runs on it (no separate mask)
+        const double b = __hiloint2double((int)bh, (int)lo[c]);
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .b32 m, t, q;\n"
+            "sub.u32 t, %1, %2;\n"
+            "setp.ge.u32 p, t, %3;\n"
+            "st.shared.f64 [%6], %5;\n"
+            "@p st.shared.f64 [%6], %4;\n"
+            "vote.sync.ballot.b32 m, p, 0xffffffff;\n"
+            "popc.b32 q, m;\n"
+            "@p and.b32 t, m, %7;\n"
+            "@p popc.b32 t, t;\n"
+            "@p mad.lo.u32 t, t, 2, %0;\n"
+            "@p st.shared.u16 [t], %8;\n"
+            "mad.lo.u32 %0, q, 2, %0;\n"
+            "}"
+            : "+r"(wq_top)
+            : "r"(bh), "n"(kCentralLo + 0x3FF00000u), "n"(kCentralSpan), "d"(b), "d"(cc[c]), "r"(slot0 + (unsigned)(kGwPB * 8 * c)), "r"(lt),
+              "h"((unsigned short)(e0 + (unsigned)(kGwPB * c)))
+            : "memory");
     }
 }
 
-// the (r x 32) block of one tile: column `col` of lane's row at buf_lane + col * kGwPB * 8
+// the warp's deferred tails [q0, q0 + 32 IL) of its queue, IL entries per lane in flight (one entry alone is a chain of
+// ~100 dependent FP64 operations).  The generator pre-filters on the high word of the uniform only, so a (rare) entry
+// may belong to the central branch after all; a lane without a further entry repeats its first one.
+template <int IL>
+__device__ __forceinline__ void gw_drain(unsigned wq_base, int q0, int wcount, unsigned tab_addr, int lane) {
+    const int qi = q0 + lane;
+    if (qi >= wcount) return;
+    unsigned a[IL];
+    double u[IL], out[IL];
+    int cls[IL];
+#pragma unroll
+    for (int c = 0; c < IL; c++) {
+        const int qc = (qi + 32 * c < wcount) ? qi + 32 * c : qi;
+        a[c] = ld_shared_u16(wq_base + 2u * qc) << 3;
+    }
+#pragma unroll
+    for (int c = 0; c < IL; c++) {
+        u[c] = __dadd_rn(ld_shared_f64(a[c]), -1.0);
+        cls[c] = ndtri_class(u[c]);
+    }
+    ndtri_tail_n<IL>(u, cls, SmemTab{tab_addr}, out);
+#pragma unroll
+    for (int c = 0; c < IL; c++) {
+        if (cls[c] == 0) out[c] = ndtri_central(u[c]);  // rare, divergent
+        st_shared_f64(a[c], out[c]);
+    }
+}
+
+// the (r x 32) block of one tile: column `col` of lane's row at buf_lane + col * kGwPB * 8.  The hash of the next
+// group of columns is issued next to the central branch of the current one (independent instruction streams in one
+// basic block).  Measured on B200: an FP64 instruction costs two issue cycles and every other instruction one, with
+// no overlap in this mix however the two streams are interleaved (forcing a fine interleave through data
+// dependences changed nothing), so what counts is the number of non-FP64 instructions per variate.
 __device__ __forceinline__ void gw_generate(unsigned long long flat, unsigned salt_base, int r, unsigned buf_lane,
                                             unsigned wq_base, unsigned lt, unsigned tab_addr, int lane) {
     unsigned wq_top = wq_base;
+    constexpr unsigned kColB = (unsigned)(kGwPB * 8);
+    const int groups = r / kGwIL;
     int col = 0;
+    if (groups > 0) {
+        unsigned hi[kGwIL], lo[kGwIL];
+        gw_hash<kGwIL>(flat, salt_base, hi, lo);
 #pragma unroll 1
-    for (; col + kGwIL <= r; col += kGwIL)
-        gw_group<kGwIL>(flat, salt_base + 8u * col, buf_lane + (unsigned)(kGwPB * 8) * col, wq_top, lt);
-#pragma unroll 1
-    for (; col < r; col++) gw_group<1>(flat, salt_base + 8u * col, buf_lane + (unsigned)(kGwPB * 8) * col, wq_top, lt);
-    __syncwarp();
-    // deferred tails, dense over the queue (see gen_slice in ttsk_sparse_pass.cuh)
-    const int wcount = (int)((wq_top - wq_base) >> 1);
-#pragma unroll 1
-    for (int qi = lane; qi < wcount; qi += 32 * kGwTailIL) {
-        unsigned a[kGwTailIL];
-        double u[kGwTailIL], out[kGwTailIL];
-        int cls[kGwTailIL];
+        for (int g = 0; g + 1 < groups; g++, col += kGwIL) {
+            unsigned hn[kGwIL], ln[kGwIL];
+            double cc[kGwIL];
+            gw_central<kGwIL>(hi, lo, cc);
+            gw_hash<kGwIL>(flat, salt_base + 8u * (col + kGwIL), hn, ln);
+            gw_store<kGwIL>(hi, lo, cc, buf_lane + kColB * col, wq_top, lt);
 #pragma unroll
-        for (int c = 0; c < kGwTailIL; c++) {
-            const int qc = (qi + 32 * c < wcount) ? qi + 32 * c : qi;
-            a[c] = ld_shared_u16(wq_base + 2u * qc) << 3;
+            for (int c = 0; c < kGwIL; c++) { hi[c] = hn[c]; lo[c] = ln[c]; }
         }
-#pragma unroll
-        for (int c = 0; c < kGwTailIL; c++) {
-            u[c] = __dadd_rn(ld_shared_f64(a[c]), -1.0);
-            cls[c] = ndtri_class(u[c]);
-        }
-        ndtri_tail_n<kGwTailIL>(u, cls, SmemTab{tab_addr}, out);
-#pragma unroll
-        for (int c = 0; c < kGwTailIL; c++) {
-            if (cls[c] == 0) out[c] = ndtri_central(u[c]);  // pre-filter is conservative by one word: rare, divergent
-            st_shared_f64(a[c], out[c]);
-        }
+        double cc[kGwIL];
+        gw_central<kGwIL>(hi, lo, cc);
+        gw_store<kGwIL>(hi, lo, cc, buf_lane + kColB * col, wq_top, lt);
+        col += kGwIL;
     }
+#pragma unroll 1
+    for (; col < r; col++) {
+        unsigned hi[1], lo[1];
+        double cc[1];
+        gw_hash<1>(flat, salt_base + 8u * col, hi, lo);
+        gw_central<1>(hi, lo, cc);
+        gw_store<1>(hi, lo, cc, buf_lane + kColB * col, wq_top, lt);
+    }
+    __syncwarp();
+    // deferred tails, dense over the queue: four entries per lane while that keeps most lanes busy, then two, then one
+    const int wcount = (int)((wq_top - wq_base) >> 1);
+    int q0 = 0;
+#pragma unroll 1
+    for (; wcount - q0 > 64; q0 += 32 * kGwTailIL) gw_drain<kGwTailIL>(wq_base, q0, wcount, tab_addr, lane);
+    if (wcount - q0 > 32) gw_drain<2>(wq_base, q0, wcount, tab_addr, lane);
+    else if (wcount - q0 > 0) gw_drain<1>(wq_base, q0, wcount, tab_addr, lane);
     __syncwarp();
 }
 

@@ -66,6 +66,8 @@ SIGNATURES = {
                                    POINTER(TtskDrm), POINTER(TtskDrm), c_void_p, c_int, c_void_p]),
     "ttsk_tt_sketch": (c_int, [c_void_p, c_int, POINTER(c_int64), POINTER(c_int32), POINTER(c_void_p), POINTER(TtskDrm),
                                POINTER(TtskDrm), c_void_p, c_void_p]),
+    "ttsk_dense_sketch": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p, POINTER(TtskDrm), POINTER(TtskDrm), c_void_p,
+                                  c_void_p]),
     "ttsk_sparse_sketch_host": (c_int, [c_void_p, c_int, POINTER(c_int64), c_int64, c_void_p, c_int64, c_void_p,
                                         POINTER(TtskDrm), POINTER(TtskDrm), c_void_p, c_int]),
     "ttsk_sparse_sketch_stream": (c_int, [c_void_p, c_int, POINTER(c_int64), c_int64, c_void_p, c_int64, c_void_p,

@@ -226,6 +226,29 @@ def _fused_tt(X: TensorTrain, left_drm: DRM, right_drm: DRM, packed):
     del lkeep, rkeep, cores
 
 
+def _fused_dense(X: DenseTensor, left_drm: DRM, right_drm: DRM, packed):
+    """One C call for a DenseTensor summand under TT DRMs (ttsk_dense_sketch): X is read once (TMA-staged first
+    pass), the left DRM is swept, the right unfoldings are used as flat arrays like the reference's dense path."""
+    x = X.device()["data"]
+    x = x if x.is_contiguous() else x.contiguous()
+    ld, lkeep = drm_descriptor(left_drm)
+    rd, rkeep = drm_descriptor(right_drm)
+    be.check(be.lib().ttsk_dense_sketch(be.ctx(), X.ndim, be.as_i64(X.shape), be.ptr(x), byref(ld), byref(rd),
+                                        be.ptr(packed), be.stream()))
+    del lkeep, rkeep, x
+
+
+def _fusable_dense(X: Tensor, left_drm: DRM, right_drm: DRM) -> bool:
+    """DenseTensor under two unsliced TensorTrainDRMs (the reference's dense sketch ignores rank slices)."""
+    if not (isinstance(X, DenseTensor) and type(left_drm) is TensorTrainDRM and type(right_drm) is TensorTrainDRM
+            and tuple(left_drm.shape) == tuple(X.shape) == tuple(right_drm.shape) and X.ndim >= 2):
+        return False
+    for drm in (left_drm, right_drm):
+        if any(int(lo) != 0 for lo in drm.bond_rank_min) or tuple(drm.bond_rank_max) != tuple(drm.bond_true_rank):
+            return False
+    return True
+
+
 def _fusable_tt(X: Tensor, left_drm: DRM, right_drm: DRM) -> bool:
     return (isinstance(X, TensorTrain) and type(left_drm) is TensorTrainDRM and type(right_drm) is TensorTrainDRM
             and tuple(left_drm.shape) == tuple(X.shape) == tuple(right_drm.shape))
@@ -258,6 +281,9 @@ def streaming_sketch_device(tensor: Tensor, left_drm: DRM, right_drm: DRM, packe
             continue
         if _fusable_tt(X, left_drm, right_drm):
             _fused_tt(X, left_drm, right_drm, packed)
+            continue
+        if _fusable_dense(X, left_drm, right_drm):
+            _fused_dense(X, left_drm, right_drm, packed)
             continue
         _check_supported(X, left_drm)
         _check_supported(X, right_drm)
