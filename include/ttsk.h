@@ -85,6 +85,13 @@ int64_t ttsk_sg_pass_count(ttsk_ctx *ctx);
 int ttsk_lazy_gaussian(ttsk_ctx *ctx, const int64_t *d_idx, int64_t idx_row_stride, int k,
                        int64_t nnz, const int64_t *h_shape, int rank_min, int rank_max,
                        uint64_t seed, double *d_out, void *stream);
+/* Sparse sign DRM rows (entries 0 / -1 / +1) for the first k index rows:
+ * replaces inds_to_sparse_sign, tt_sketch/drm/fast_lazy_gaussian.pyx:121-180 (called from
+ * SparseSignDRM.sketch_sparse, tt_sketch/drm/sparse_sign_drm.py:34-51).  d_out is (nnz, rank_max - rank_min)
+ * row-major FP64: columns [rank_min, rank_max) of the (nnz, rank) matrix whose rows hold nnz_row non-zeros. */
+int ttsk_lazy_sparse_sign(ttsk_ctx *ctx, const int64_t *d_idx, int64_t idx_row_stride, int k, int64_t nnz,
+                          const int64_t *h_shape, int rank, int rank_min, int rank_max, int nnz_row,
+                          uint64_t seed, double *d_out, void *stream);
 
 /* Self-test of the straight-line FP64 division used inside the generator: counts operand
  * pairs (n pseudo-random pairs from `seed`, magnitudes 2^-30..2^10 and zero numerators) whose

@@ -195,3 +195,35 @@ void ora_inds_to_normal(const uint64_t *idx, int k, int64_t nnz, const uint64_t 
         }
     }
 }
+
+/* ---- sparse sign DRM ---- tt_sketch/drm/fast_lazy_gaussian.pyx:121-180 (_inds_to_sparse_sign, inds_to_sparse_sign)
+ * Per nonzero: nnz_row hashed doubles d_j (the Gaussian DRM's hash with the top bits forced to 001, columns
+ * 0..nnz_row-1, .pyx:52-105).  frexp(d_j) splits each into the exponent e, whose parity gives the sign
+ * (e % 2) * 2 - 1 -- Cython gives `%` on C ints PYTHON semantics (cdivision is off), so the entries are -1 / +1; the
+ * exponent field is hash bits 52..60 under the forced 01, so the parity is hash bit 52 -- and the mantissa
+ * m * 2 - 1 (the low 52 hash bits as a uniform), which drives a partial Fisher-Yates shuffle of the row.
+ * out is (nnz, rank_max - rank_min) row-major int16 (0 / -1 / +1) like the reference's return value. */
+void ora_inds_to_sparse_sign(const uint64_t *idx, int k, int64_t nnz, const uint64_t *shape, int rank, int rank_min,
+                             int rank_max, int nnz_row, uint64_t seed, int16_t *out) {
+    int16_t row[4096];
+    double mant[4096];
+    int width = rank_max - rank_min;
+    for (int64_t p = 0; p < nnz; p++) {
+        uint64_t flat = flat_index(idx, k, nnz, shape, p);
+        for (int j = 0; j < rank; j++) row[j] = 0;
+        for (int j = 0; j < nnz_row; j++) {
+            uint64_t salt = ora_hash64((uint64_t)j) + seed;
+            uint64_t h = (ora_hash64(flat + salt) | 0x2000000000000000ULL) & 0x3FFFFFFFFFFFFFFFULL;
+            int e;
+            mant[j] = frexp(bits2d(h), &e) * 2 - 1;
+            row[j] = (int16_t)((((e % 2) + 2) % 2) * 2 - 1);  /* Python-style remainder */
+        }
+        for (int j = 0; j < nnz_row; j++) {
+            int rn = (int)(mant[j] * (rank - j) + j);
+            int16_t t = row[j];
+            row[j] = row[rn];
+            row[rn] = t;
+        }
+        for (int a = 0; a < width; a++) out[p * width + a] = row[rank_min + a];
+    }
+}

@@ -240,14 +240,54 @@ def gen_stt_ops():
     print("stt_ops.npz")
 
 
+def gen_sparse_sign():
+    """SparseSignDRM (sparse_sign_drm.py:12-51, fast_lazy_gaussian.pyx:121-180 of the reference): raw
+    inds_to_sparse_sign outputs (int16: 0 / -1 / +1) incl. rank slices, fewer non-zeros than columns and the int32
+    stride wrap, and one stream_sketch of a sparse tensor under SparseSignDRMs."""
+    from tt_sketch.drm import SparseSignDRM
+    from tt_sketch.drm.fast_lazy_gaussian import inds_to_sparse_sign
+
+    rng = np.random.default_rng(777)
+    store, cases, n = {}, [], 0
+    for shape in [(10, 12, 14, 7), (70000, 70000, 3), (10000, 10000, 10000, 500)]:
+        for k in range(1, len(shape) + 1):
+            for (rank, rmin, rmax, nzr) in [(17, 0, 17, 17), (17, 5, 17, 17), (17, 0, 9, 6), (40, 12, 33, 40), (8, 0, 8, 1)]:
+                for seed in (5, 179):
+                    nnz = 40
+                    idx = np.stack([rng.integers(0, m, nnz) for m in shape[:k]]).astype(np.int64)
+                    g = np.asarray(inds_to_sparse_sign(idx, shape[:k], rank, rmin, rmax, nzr, seed))
+                    store[f"c{n}_idx"] = idx
+                    store[f"c{n}_out"] = g.astype(np.int16)
+                    cases.append((len(shape),) + tuple(shape) + (0,) * (4 - len(shape)) + (k, rank, rmin, rmax, nzr, seed))
+                    n += 1
+    store["cases"] = np.array(cases, dtype=np.int64)
+    shape = (7, 8, 9, 10)
+    sp = make_sparse(shape, 300, 1)
+    lrank, rrank = (3, 4, 5), (5, 6, 7)
+    tensor_pack("sk_T", sp, store)
+    left = SparseSignDRM(lrank, shape=shape, transpose=False, seed=11)
+    right = SparseSignDRM(rrank, shape=shape, transpose=True, seed=23, num_non_zero_per_row=(3, 4, 2))
+    stt = stream_sketch(sp, lrank, rrank, left_drm=left, right_drm=right)
+    sketch_pack("sk", stt.Psi_cores, stt.Omega_mats, store)
+    store["sk_right_nnz"] = np.array((3, 4, 2), dtype=np.int64)
+    store["lrank"] = np.array(lrank, dtype=np.int64)
+    store["rrank"] = np.array(rrank, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "sparse_sign.npz"), **store)
+    print("sparse_sign.npz:", n, "cases")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "stt_ops":  # later additions leave the earlier fixtures untouched
         gen_stt_ops()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "sparse_sign":
+        gen_sparse_sign()
         sys.exit(0)
     gen_lazy_gaussian()
     gen_sketches()
     gen_ttdrm_cores()
     gen_stt_ops()
+    gen_sparse_sign()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")

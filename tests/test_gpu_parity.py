@@ -261,3 +261,34 @@ def test_sparse_duplicates_empty_slices_and_ragged_segments(oracle_lib):
             assert rel_err(a, b) < TOL, nnz
         for a, b in zip(sk.Omega_mats, Om):
             assert rel_err(a, b) < TOL, nnz
+
+
+def test_sparse_sign_drm_bit_exact_and_sketch_vs_golden():
+    """SparseSignDRM: ttsk_lazy_sparse_sign == the reference's inds_to_sparse_sign entry for entry
+    (integers: exact), and stream_sketch under SparseSignDRMs == the reference's Psi / Omega."""
+    from tt_sketch import _backend as be
+    from tt_sketch.drm import SparseSignDRM
+    from tt_sketch.sketch import stream_sketch
+
+    z = load("sparse_sign.npz")
+    for n, c in enumerate(z["cases"]):
+        d = int(c[0]); shape = tuple(int(x) for x in c[1:1 + d]); k, rank, rmin, rmax, nzr, seed = (int(x) for x in c[5:])
+        idx = z[f"c{n}_idx"]
+        got = be.to_host(be.lazy_sparse_sign(be.to_device(idx, np.int64), k, idx.shape[1], shape, rank, rmin, rmax, nzr, seed))
+        assert np.array_equal(got, z[f"c{n}_out"].astype(np.float64)), n
+    t = tensor_desc(z, "sk_T")
+    X = make_tensor(t)
+    lr, rr = tuple(int(x) for x in z["lrank"]), tuple(int(x) for x in z["rrank"])
+    left = SparseSignDRM(lr, shape=t[1], transpose=False, seed=11)
+    right = SparseSignDRM(rr, shape=t[1], transpose=True, seed=23, num_non_zero_per_row=tuple(int(x) for x in z["sk_right_nnz"]))
+    stt = stream_sketch(X, lr, rr, left_drm=left, right_drm=right)
+    for i, a in enumerate(stt.Psi_cores):
+        assert rel_err(a, z[f"sk_Psi{i}"]) < TOL
+    for i, a in enumerate(stt.Omega_mats):
+        assert rel_err(a, z[f"sk_Omega{i}"]) < TOL
+    # slices (blocked sketches) pick columns of the same matrix
+    sl = left.slice((1, 1, 2), (3, 4, 5))
+    full = [be.to_host(m) for m in left.sketch_sparse_device(X)]
+    part = [be.to_host(m) for m in sl.sketch_sparse_device(X)]
+    for mu, (lo, hi) in enumerate(zip((1, 1, 2), (3, 4, 5))):
+        assert np.array_equal(part[mu], full[mu][lo:hi])

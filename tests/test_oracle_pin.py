@@ -144,3 +144,26 @@ def test_oracle_matches_reference_stt_ops_golden():
         assert rel_err(a, w) < 1e-12
     for a, w in zip(O, stored_list(z, "gauss_inc_Omega")):
         assert rel_err(a, w) < 1e-12
+
+
+def test_sparse_sign_oracle_matches_reference_goldens(oracle_lib):
+    """inds_to_sparse_sign restatement == the reference's int16 output (fast_lazy_gaussian.pyx:121-180) on 110 fixed
+    cases: rank slices, fewer non-zeros than columns, the int32 stride wrap; and a whole stream_sketch under
+    SparseSignDRMs (sparse_sign_drm.py:34-51)."""
+    from _golden import load, rel_err, tensor_desc
+    from oracle import sketch_oracle as orc
+
+    z = load("sparse_sign.npz")
+    for n, c in enumerate(z["cases"]):
+        d = int(c[0]); shape = tuple(int(x) for x in c[1:1 + d]); k, rank, rmin, rmax, nzr, seed = (int(x) for x in c[5:])
+        got = orc.inds_to_sparse_sign(z[f"c{n}_idx"], shape[:k], rank, rmin, rmax, nzr, seed)
+        assert np.array_equal(got, z[f"c{n}_out"]), n
+    t = tensor_desc(z, "sk_T")
+    lr, rr = tuple(int(x) for x in z["lrank"]), tuple(int(x) for x in z["rrank"])
+    L = orc.Drm("sign", False, t[1], (0,) * 3, lr, 11)
+    R = orc.Drm("sign", True, t[1], (0,) * 3, rr, 23, nnz_row=tuple(int(x) for x in z["sk_right_nnz"])[::-1])
+    Psi, Om = orc.general_sketch(t, L, R, "streaming")
+    for i, a in enumerate(Psi):
+        assert rel_err(a, z[f"sk_Psi{i}"]) < 1e-12
+    for i, a in enumerate(Om):
+        assert rel_err(a, z[f"sk_Omega{i}"]) < 1e-12

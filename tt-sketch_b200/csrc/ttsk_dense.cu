@@ -189,16 +189,27 @@ __global__ void __launch_bounds__(kFpThreads, 1)
         if (tid == 0 && t + kFpStages * dt < A.n_tiles) issue(t + kFpStages * dt, s);
         if (++s == kFpStages) { s = 0; ph ^= 1u; }
     }
+    // Y0: the warps' partial sums (each warp covered its own k-steps) are added up in shared memory, so a CTA sends
+    // ONE atomic per element of the small (n0 x rR) matrix (all CTAs add into the same few hundred addresses)
+    __syncthreads();  // every TMA load has been consumed: the stage buffers are free
+    double* ysum = reinterpret_cast<double*>(xs);  // [kFpWarps][8 MR][8 NJ]
+    constexpr int YP = 8 * NJ;
 #pragma unroll
     for (int i = 0; i < MR; i++)
 #pragma unroll
         for (int j = 0; j < NJ; j++) {
-            const int row = 8 * i + g, col = 8 * j + 2 * q;
-            if (row < n0) {
-                if (col < A.rR && yacc[i][j][0] != 0.0) atomicAdd(A.Y0 + (long long)row * A.rR + col, yacc[i][j][0]);
-                if (col + 1 < A.rR && yacc[i][j][1] != 0.0) atomicAdd(A.Y0 + (long long)row * A.rR + col + 1, yacc[i][j][1]);
-            }
+            double* dst = ysum + ((size_t)warp * 8 * MR + 8 * i + g) * YP + 8 * j + 2 * q;
+            dst[0] = yacc[i][j][0];
+            dst[1] = yacc[i][j][1];
         }
+    __syncthreads();
+    for (int e = tid; e < n0 * A.rR; e += kFpThreads) {
+        const int row = e / A.rR, col = e - row * A.rR;
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < kFpWarps; w++) sum += ysum[((size_t)w * 8 * MR + row) * YP + col];
+        if (sum != 0.0) atomicAdd(A.Y0 + (long long)row * A.rR + col, sum);
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

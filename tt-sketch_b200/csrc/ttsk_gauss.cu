@@ -72,6 +72,38 @@ int gauss_table_launch(ttsk_ctx* ctx, int64_t rows, int rank_min, int rank, uint
     return gauss_rows_launch(ctx, gi, rows, rank_min, rank, seed, d_out, st);
 }
 
+// ------------------------------------------------------------------ sparse sign DRM
+// Replaces inds_to_sparse_sign / _inds_to_sparse_sign, tt_sketch/drm/fast_lazy_gaussian.pyx:121-180: per nonzero,
+// nnz_row hashed doubles (the Gaussian DRM's hash with the top bits forced to 001, columns 0..nnz_row-1); frexp
+// splits each into an exponent whose parity is the sign (Python-style e % 2: hash bit 52, entries -1 / +1) and a
+// mantissa m * 2 - 1 (the low 52 hash bits as a uniform) that drives a partial Fisher-Yates shuffle of the row.
+// One thread per nonzero; the row lives in local memory.  out is (nnz, rank_max - rank_min) row-major FP64 (what
+// the sketching operators consume).
+constexpr int kMaxSignRank = 512;
+
+__global__ void __launch_bounds__(128) lazy_sparse_sign_kernel(GaussIdx gi, long long nnz, int rank, int rank_min, int width,
+                                                              int nnz_row, unsigned long long seed, double* __restrict__ out) {
+    short row[kMaxSignRank];
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (long long)gridDim.x * blockDim.x) {
+        unsigned long long flat = (unsigned long long)gi.rows[0][p];
+        for (int i = 1; i < gi.k; i++) flat += (unsigned long long)gi.rows[i][p] * (unsigned long long)gi.strides[i];
+        for (int j = 0; j < rank; j++) row[j] = 0;
+        for (int j = 0; j < nnz_row; j++) {
+            const unsigned long long h = hash64(flat + hash64((unsigned long long)j) + seed);
+            row[j] = (short)((int)((h >> 52) & 1ull) * 2 - 1);  // parity of the forced-001 double's frexp exponent
+        }
+        for (int j = 0; j < nnz_row; j++) {
+            const double m = uniform_from_hash(hash64(flat + hash64((unsigned long long)j) + seed));  // frexp mantissa * 2 - 1
+            int rn = __double2int_rz(__dadd_rn(__dmul_rn(m, (double)(rank - j)), (double)j));
+            rn = rn < 0 ? 0 : (rn >= rank ? rank - 1 : rn);
+            const short t = row[j];
+            row[j] = row[rn];
+            row[rn] = t;
+        }
+        for (int a = 0; a < width; a++) out[p * width + a] = (double)row[rank_min + a];
+    }
+}
+
 // self-test: div_rn_safe vs __ddiv_rn on pseudo-random operands in the ranges ndtri uses
 __global__ void selftest_div_kernel(long long n, unsigned long long seed, unsigned long long* mismatches) {
     unsigned long long bad = 0;
@@ -128,6 +160,28 @@ extern "C" int ttsk_selftest_div(ttsk_ctx* ctx, int64_t n, uint64_t seed, uint64
     TTSK_LAUNCHED(ctx);
     TTSK_CUDA(cudaMemcpy(h_mismatches, d, 8, cudaMemcpyDeviceToHost));
     TTSK_CUDA(cudaFree(d));
+    return TTSK_OK;
+}
+
+extern "C" int ttsk_lazy_sparse_sign(ttsk_ctx* ctx, const int64_t* d_idx, int64_t idx_row_stride, int k, int64_t nnz,
+                                     const int64_t* h_shape, int rank, int rank_min, int rank_max, int nnz_row,
+                                     uint64_t seed, double* d_out, void* stream) {
+    TTSK_ARG(ctx != nullptr, "ctx is NULL");
+    TTSK_ARG(k >= 1 && k <= TTSK_MAX_ORDER, "k out of range");
+    TTSK_ARG(nnz >= 0 && rank_max >= rank_min && rank_min >= 0 && rank_max <= rank, "nnz/rank range");
+    TTSK_ARG(rank >= 1 && rank <= ttsk::kMaxSignRank, "sparse sign DRM: rank must be in [1, 512]");
+    TTSK_ARG(nnz_row >= 1 && nnz_row <= rank, "sparse sign DRM: non-zeros per row must be in [1, rank]");
+    TTSK_ARG(h_shape != nullptr && (nnz == 0 || (d_idx && d_out)), "NULL pointer");
+    if (nnz == 0 || rank_max == rank_min) return TTSK_OK;
+    ttsk::GaussIdx gi;
+    gi.k = k;
+    for (int i = 0; i < k; i++) gi.rows[i] = (const long long*)(d_idx + i * idx_row_stride);
+    ttsk::wrapped_strides(h_shape, k, gi.strides);
+    long long blocks = (nnz + 127) / 128;
+    if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
+    ttsk::lazy_sparse_sign_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(gi, nnz, rank, rank_min, rank_max - rank_min,
+                                                                                     nnz_row, seed, d_out);
+    TTSK_LAUNCHED(ctx);
     return TTSK_OK;
 }
 

@@ -188,6 +188,127 @@ __global__ void __launch_bounds__(1024) scatter_local_kernel(const ScatterParams
     }
 }
 
+// ------------------------------------------------------------------ two-level partition (n_mu <= 16384)
+// Bucketing as two partition sweeps: first by key >> 7 (at most 128 coarse buckets), then, tile by tile inside a coarse
+// bucket, by the full key.  A tile of 4096 elements is ranked per digit with shared-memory counters, reserves its
+// space in every destination bucket with one global atomic per non-empty digit, and writes runs of consecutive
+// elements (about 50 words per coarse bucket in the first sweep, 32 per key in the second) -- against single
+// 8-byte words into 10^4 x CTAs open ranges in the one-sweep scatter above.  Traffic: keys read twice (histogram,
+// sweep 1), words written and read once more: 4 GB at nnz = 1e8.
+constexpr int kPartTile = 4096, kPartThreads = 512, kPartBins = 128, kPartPer = kPartTile / kPartThreads;
+
+// the tile map of the second sweep: coarse bucket b owns keys [128 b, 128 b + 128)
+__global__ void __launch_bounds__(kPartBins) part_setup_kernel(const int* __restrict__ offs, int n_mu, int* __restrict__ tstart) {
+    __shared__ int s_t[kPartBins];
+    const int b = threadIdx.x;
+    const int k0 = min(b * kPartBins, n_mu), k1 = min((b + 1) * kPartBins, n_mu);
+    const int lo = offs[k0], hi = offs[k1];
+    s_t[b] = (hi - lo + kPartTile - 1) / kPartTile;
+    __syncthreads();
+    if (b == 0) {
+        int run = 0;
+        for (int i = 0; i < kPartBins; i++) { const int t = s_t[i]; tstart[i] = run; run += t; }
+        tstart[kPartBins] = run;
+    }
+}
+
+// start of (CTA c, coarse bucket b) in the first sweep's output, from the per-(CTA, key) range starts of the final
+// layout (cta_base_kernel): bucket b begins at offs[128 b] and CTA c's share of it follows the shares of the CTAs
+// before it.  With these the first sweep needs no global atomics (79 hot cursors hit by every tile cost 1 ms).
+__global__ void __launch_bounds__(kPartBins) part_l1base_kernel(const int* __restrict__ cta_base, const int* __restrict__ offs,
+                                                                int n_mu, int* __restrict__ l1base) {
+    const int c = blockIdx.x, b = threadIdx.x;
+    const int k0 = min(b * kPartBins, n_mu), k1 = min((b + 1) * kPartBins, n_mu);
+    int before = 0;
+    for (int k = k0; k < k1; k++) before += cta_base[(long long)c * n_mu + k] - offs[k];
+    l1base[c * kPartBins + b] = offs[k0] + before;
+}
+
+// LEVEL 1: CTA c walks ITS block of the nonzeros (the block the histogram kernel counted for it) in input order,
+//          digit = key >> 7, destination = the CTA's own cursor of the coarse bucket (shared memory, no atomics).
+// LEVEL 2: elements are the words of the first sweep, walked per coarse bucket (tile map `tstart`), digit = key & 127,
+//          destination cursor cursor[key].
+template <int LEVEL>
+__global__ void __launch_bounds__(kPartThreads) partition_kernel(const long long* __restrict__ keys,
+                                                                const unsigned long long* __restrict__ in_words, long long n,
+                                                                int n_mu, const int* __restrict__ offs,
+                                                                const int* __restrict__ tstart, int* __restrict__ cursors,
+                                                                unsigned long long* __restrict__ out_words, long long block_len) {
+    __shared__ int s_cnt[kPartBins];
+    __shared__ int s_base[kPartBins];
+    __shared__ int s_cur[kPartBins];
+    __shared__ long long s_range[2];
+    __shared__ int s_bucket;
+    const int tid = threadIdx.x;
+    // LEVEL 1: tiles of this CTA's block; LEVEL 2: tiles of the whole array, strided over the grid
+    const long long blk_lo = (long long)blockIdx.x * block_len, blk_hi = (blk_lo + block_len < n) ? blk_lo + block_len : n;
+    const long long n_tiles = (LEVEL == 1) ? (blk_hi > blk_lo ? (blk_hi - blk_lo + kPartTile - 1) / kPartTile : 0) : (long long)tstart[kPartBins];
+    if (LEVEL == 1 && tid < kPartBins) s_cur[tid] = cursors[blockIdx.x * kPartBins + tid];
+    for (long long t = (LEVEL == 1) ? 0 : blockIdx.x; t < n_tiles; t += (LEVEL == 1) ? 1 : gridDim.x) {
+        if (tid < kPartBins) s_cnt[tid] = 0;
+        if (tid == 0) {
+            if (LEVEL == 1) {
+                s_range[0] = blk_lo + t * kPartTile;
+                s_range[1] = (s_range[0] + kPartTile < blk_hi) ? s_range[0] + kPartTile : blk_hi;
+                s_bucket = 0;
+            } else {
+                int lo = 0, hi = kPartBins - 1;  // last bucket b with tstart[b] <= t
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if ((long long)tstart[mid] <= t) lo = mid; else hi = mid - 1;
+                }
+                const int k0 = min(lo * kPartBins, n_mu), k1 = min((lo + 1) * kPartBins, n_mu);
+                const long long b_lo = offs[k0], b_hi = offs[k1];
+                s_range[0] = b_lo + (t - tstart[lo]) * kPartTile;
+                s_range[1] = (s_range[0] + kPartTile < b_hi) ? s_range[0] + kPartTile : b_hi;
+                s_bucket = lo;
+            }
+        }
+        __syncthreads();
+        const long long lo = s_range[0], hi = s_range[1];
+        unsigned long long w[kPartPer];
+        int rank[kPartPer];
+#pragma unroll
+        for (int u = 0; u < kPartPer; u++) {
+            const long long p = lo + tid + (long long)u * kPartThreads;
+            if (p < hi) {
+                if (LEVEL == 1) w[u] = ((unsigned long long)(unsigned)__ldcs(keys + p) << 32) | (unsigned long long)(unsigned)p;
+                else w[u] = __ldcs(in_words + p);
+            } else {
+                w[u] = ~0ull;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kPartPer; u++) {
+            if (w[u] != ~0ull) {
+                const int key = (int)(w[u] >> 32);
+                const int dgt = (LEVEL == 1) ? (key >> 7) : (key & (kPartBins - 1));
+                rank[u] = atomicAdd(&s_cnt[dgt], 1);
+            }
+        }
+        __syncthreads();
+        if (tid < kPartBins) {
+            const int c = s_cnt[tid];
+            if (LEVEL == 1) {
+                s_base[tid] = s_cur[tid];
+                s_cur[tid] += c;
+            } else if (c) {
+                s_base[tid] = atomicAdd(&cursors[s_bucket * kPartBins + tid], c);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kPartPer; u++) {
+            if (w[u] != ~0ull) {
+                const int key = (int)(w[u] >> 32);
+                const int dgt = (LEVEL == 1) ? (key >> 7) : (key & (kPartBins - 1));
+                out_words[s_base[dgt] + rank[u]] = w[u];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ TT-DRM chain step
 // v_out[p, b] = sum_a v_in[p, a] * core[a, idx[p], b]   (first core: v_out[p, b] = core[0, idx[p], b])
 __global__ void __launch_bounds__(256) ttdrm_step_kernel(long long nnz, const long long* __restrict__ idx,
@@ -370,6 +491,8 @@ static int launch_pass(ttsk_ctx* ctx, PassParams& P, bool has_x, cudaStream_t st
 struct SortBufs {
     int* hist; int* offs; int* cursor;
     int* cta_cnt;  // per-CTA key counts / range starts of the two-level scatter
+    unsigned long long* part_tmp;  // words after the first sweep of the two-level partition
+    int* part_aux;                 // tile map of the second sweep [129], then the (CTA, coarse bucket) starts of the first [CTAs][128]
     // TT DRMs bucket a mode up to three times (chain level of either side + the mode pass): with n_modes > 0 every
     // mode keeps its own sorted words / segment starts for the chunk and is bucketed once
     int n_modes = 0;
@@ -384,8 +507,8 @@ static int rec_words_for(int d) { return d <= 0 ? 0 : (int)align_up(2 + d, 8); }
 constexpr int kMaxSortCtas = 2 * 160;  // the two-level scatter runs two CTAs per SM
 static int64_t cta_cnt_bytes(int64_t n_max) { return n_max <= kLocalBins ? (int64_t)kMaxSortCtas * n_max * 4 : 256; }
 static int64_t sortbufs_bytes(int64_t n_max, int64_t chunk, int d, int per_mode = 0) {
-    return 3 * align_up((n_max + 1) * 4, 256) + align_up(chunk * 8, 256) + align_up(chunk * 4 * rec_words_for(d), 256) +
-           align_up(cta_cnt_bytes(n_max), 256) + 2048 +
+    return 3 * align_up((n_max + 1) * 4, 256) + 2 * align_up(chunk * 8, 256) + align_up(chunk * 4 * rec_words_for(d), 256) +
+           align_up(cta_cnt_bytes(n_max), 256) + 4096 + align_up((128 + 8 + (int64_t)kMaxSortCtas * 128) * 4, 256) +
            (per_mode ? (int64_t)d * (align_up(chunk * 8, 256) + align_up((n_max + 1) * 4, 256)) : 0);
 }
 static int carve_sortbufs(ttsk_ctx* ctx, SortBufs& sb, int64_t n_max, int64_t chunk, int d, int per_mode = 0) {
@@ -410,7 +533,9 @@ static int carve_sortbufs(ttsk_ctx* ctx, SortBufs& sb, int64_t n_max, int64_t ch
     sb.cursor = (int*)ctx->ws_alloc((n_max + 1) * 4);
     sb.keyid = (unsigned long long*)ctx->ws_alloc(chunk * 8);
     sb.cta_cnt = (int*)ctx->ws_alloc(cta_cnt_bytes(n_max));
-    if (!sb.hist || !sb.offs || !sb.cursor || !sb.keyid || !sb.cta_cnt) {
+    sb.part_tmp = (unsigned long long*)ctx->ws_alloc(chunk * 8);
+    sb.part_aux = (int*)ctx->ws_alloc((kPartBins + 8 + (int64_t)kMaxSortCtas * kPartBins) * 4);
+    if (!sb.hist || !sb.offs || !sb.cursor || !sb.keyid || !sb.cta_cnt || !sb.part_tmp || !sb.part_aux) {
         set_error("workspace carve failed (sort buffers)");
         return TTSK_E_NOMEM;
     }
@@ -432,6 +557,8 @@ static int sort_keys(ttsk_ctx* ctx, int64_t nnz, const long long* key_idx, int64
     if (block_len < 65536) block_len = 65536;
     const long long local_grid = (nnz + block_len - 1) / block_len;
     const bool local = n_mu <= kLocalBins && nnz >= 65536 && local_grid <= kMaxSortCtas;
+    static const int part_off = getenv("TTSK_SORT_ONE_SWEEP") ? atoi(getenv("TTSK_SORT_ONE_SWEEP")) : 0;
+    const bool two_level = local && !part_off && n_mu <= kPartBins * kPartBins && nnz < ((int64_t)1 << 31);
     TTSK_CUDA(cudaMemsetAsync(sb.hist, 0, (size_t)n_mu * sizeof(int), st));
     if (local) {
         const size_t smem = (size_t)n_mu * 4;
@@ -448,6 +575,23 @@ static int sort_keys(ttsk_ctx* ctx, int64_t nnz, const long long* key_idx, int64
     S.key_idx = key_idx;
     S.cursor = sb.cursor;
     S.keyid = sb.keyid;
+    if (two_level) {
+        int* tstart = sb.part_aux;
+        int* l1base = sb.part_aux + kPartBins + 8;
+        cta_base_kernel<<<(unsigned)((n_mu + 255) / 256), 256, 0, st>>>(sb.cta_cnt, sb.offs, (int)n_mu, (int)local_grid);
+        TTSK_LAUNCHED(ctx);
+        part_l1base_kernel<<<(unsigned)local_grid, kPartBins, 0, st>>>(sb.cta_cnt, sb.offs, (int)n_mu, l1base);
+        TTSK_LAUNCHED(ctx);
+        part_setup_kernel<<<1, kPartBins, 0, st>>>(sb.offs, (int)n_mu, tstart);
+        TTSK_LAUNCHED(ctx);
+        partition_kernel<1><<<(unsigned)local_grid, kPartThreads, 0, st>>>(key_idx, nullptr, nnz, (int)n_mu, sb.offs, tstart, l1base,
+                                                                          sb.part_tmp, block_len);
+        TTSK_LAUNCHED(ctx);
+        const unsigned grid = (unsigned)std::min<long long>((nnz + kPartTile - 1) / kPartTile, 4LL * ctx->sm_count);
+        partition_kernel<2><<<grid, kPartThreads, 0, st>>>(nullptr, sb.part_tmp, nnz, (int)n_mu, sb.offs, tstart, sb.cursor, sb.keyid, 0);
+        TTSK_LAUNCHED(ctx);
+        return TTSK_OK;
+    }
     if (local) {
         const size_t smem = (size_t)n_mu * 8;
         TTSK_CUDA(cudaFuncSetAttribute(scatter_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

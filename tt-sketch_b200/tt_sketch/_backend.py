@@ -59,6 +59,8 @@ SIGNATURES = {
     "ttsk_trim": (c_int, [c_void_p]),
     "ttsk_lazy_gaussian": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, POINTER(c_int64), c_int, c_int,
                                    c_uint64, c_void_p, c_void_p]),
+    "ttsk_lazy_sparse_sign": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, POINTER(c_int64), c_int, c_int, c_int, c_int,
+                                      c_uint64, c_void_p, c_void_p]),
     "ttsk_selftest_div": (c_int, [c_void_p, c_int64, c_uint64, POINTER(c_uint64)]),
     "ttsk_selftest_sqrt": (c_int, [c_void_p, c_int64, c_uint64, POINTER(c_uint64)]),
     "ttsk_sketch_size": (c_int64, [c_int, POINTER(c_int64), POINTER(c_int32), POINTER(c_int32)]),
@@ -270,6 +272,14 @@ def lazy_gaussian(d_idx, k: int, nnz: int, shape, rank_min: int, rank_max: int, 
     out = empty((nnz, rank_max - rank_min))
     check(lib().ttsk_lazy_gaussian(ctx(), ptr(d_idx), d_idx.stride(0), k, nnz, as_i64(shape[:k]), int(rank_min),
                                    int(rank_max), int(seed) % 2**63, ptr(out), stream()))
+    return out
+
+
+def lazy_sparse_sign(d_idx, k: int, nnz: int, shape, rank: int, rank_min: int, rank_max: int, nnz_row: int, seed: int):
+    """Device (nnz, rank_max - rank_min) sparse-sign rows for the first k index rows of d_idx (k x nnz int64)."""
+    out = empty((nnz, rank_max - rank_min))
+    check(lib().ttsk_lazy_sparse_sign(ctx(), ptr(d_idx), d_idx.stride(0), k, nnz, as_i64(shape[:k]), int(rank), int(rank_min),
+                                      int(rank_max), int(nnz_row), int(seed) % 2**63, ptr(out), stream()))
     return out
 
 
