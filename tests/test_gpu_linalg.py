@@ -52,16 +52,29 @@ def test_pinv(m, n):
         assert _rel(got2 @ A2 @ got2, got2) < 1e-3 and np.linalg.norm(got2, 2) > 1e11
 
 
-@pytest.mark.parametrize("m,n", [(1000, 20), (50, 50), (37, 5), (5, 1), (20000, 40)])
+@pytest.mark.parametrize("m,n", [(1000, 20), (50, 50), (37, 5), (5, 1), (20000, 40), (200000, 40), (9001, 64), (8192, 1), (30000, 33)])
 def test_qr_matches_lapack(m, n):
     from tt_sketch import _backend as be
 
     rng = np.random.default_rng(2)
     A = rng.standard_normal((m, n))
     q_want, _ = scipy.linalg.qr(A, mode="economic")
-    q = be.to_host(be.qr_q_inplace(be.to_device(A.copy())))
+    q = be.to_host(be.qr_q_inplace(be.to_device(A.copy())))   # m >= 8192: the grid-cooperative kernel (one row block per SM)
     assert _rel(q, q_want) < 1e-11
     assert np.allclose(q.T @ q, np.eye(n), atol=1e-12)
+
+
+def test_qr_grid_kernel_handles_dependent_columns():
+    """A zero column (tau = 0) and an exactly dependent column in a tall panel: same Q as LAPACK where it is determined."""
+    from tt_sketch import _backend as be
+
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((10000, 6))
+    A[:, 2] = 0.0
+    q_want, _ = scipy.linalg.qr(A, mode="economic")
+    q = be.to_host(be.qr_q_inplace(be.to_device(A.copy())))
+    assert _rel(q[:, :2], q_want[:, :2]) < 1e-11
+    assert np.allclose(q.T @ q, np.eye(6), atol=1e-10)
 
 
 def test_orth_step_matches_reference_formula():

@@ -9,6 +9,7 @@
 // (one-sided Jacobi SVD, singular values below rcond*s_max dropped like gelsd) and applied to
 // the (r*n) right-hand sides with ttsk_gemm.
 #include <cfloat>
+#include <cstdlib>
 
 #include "ttsk_common.cuh"
 
@@ -215,6 +216,135 @@ __global__ void __launch_bounds__(1024) householder_q_kernel(double* __restrict_
     }
 }
 
+// ------------------------------------------------------------------ the same QR over the whole GPU
+// Tall panels (the (r n) x r unfoldings of orth_step at n = 10^4 ... have 10^5 rows) on ONE SM stream the panel
+// through a single CTA 2 n times.  Here every CTA owns a block of rows (L2-resident) and the n Householder steps run
+// in lock step: per column one grid-wide reduction for the norm and one for the n - j - 1 products v^T A[:, c]
+// (FP64 atomics into per-column slots, then a grid barrier), and one more per column when Q is formed backwards.
+// The arithmetic is dgeqr2 / dorg2r's (same reflectors, same signs: Q matches scipy.linalg.qr), only the
+// summation order of the reductions differs.  Launched cooperatively (all CTAs co-resident).
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, unsigned n_cta) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        epoch += n_cta;
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile unsigned*>(counter) < epoch) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+constexpr int kQrThreads = 512;
+
+// red: [n] squared norms, [n][n] forward products, [n][n] backward products (zero on entry); bar: zero on entry
+__global__ void __launch_bounds__(kQrThreads, 1) householder_q_grid_kernel(double* __restrict__ A, long long m, int n,
+                                                                         long long rows_per_cta, double* __restrict__ red,
+                                                                         unsigned* __restrict__ bar) {
+    __shared__ double s_part[kQrThreads / 32][65];
+    __shared__ double s_tw[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kQrThreads / 32;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = (r0 + rows_per_cta < m) ? r0 + rows_per_cta : m;
+    double* nrm = red;
+    double* fwd = red + n;
+    double* bwd = fwd + (long long)n * n;
+    double* taus = bwd + (long long)n * n;  // written redundantly by every CTA (same values)
+    unsigned epoch = 0;
+    const unsigned n_cta = gridDim.x;
+    // products of column j with columns c in (j, n) over this CTA's rows i >= lo: lane = column (two columns per lane
+    // for n <= 64), warps stride the rows; v_i = A[i][j] * scale (and 1 for the pivot row when unit_pivot)
+    auto column_products = [&](int j, long long lo, double scale, bool unit_pivot, bool scale_in_place, double* out) {
+        const int c0 = j + 1 + lane, c1 = j + 33 + lane;
+        double w0 = 0.0, w1 = 0.0;
+        for (long long i = (lo > r0 ? lo : r0) + warp; i < r1; i += nwarps) {
+            double v = A[i * n + j];
+            if (unit_pivot && i == j) v = 1.0;
+            else {
+                v *= scale;
+                if (scale_in_place && lane == 0) A[i * n + j] = v;
+            }
+            if (c0 < n) w0 = fma(v, A[i * n + c0], w0);
+            if (c1 < n) w1 = fma(v, A[i * n + c1], w1);
+        }
+        s_part[warp][lane] = w0;
+        s_part[warp][32 + lane] = w1;
+        __syncthreads();
+        if (tid < 64 && j + 1 + tid < n) {
+            double t = 0.0;
+            for (int w = 0; w < nwarps; w++) t += s_part[w][tid];
+            if (t != 0.0) atomicAdd(out + j + 1 + tid, t);
+        }
+        __syncthreads();
+    };
+    for (int j = 0; j < n; j++) {
+        // ---- dlarfg on column j, rows j .. m-1
+        double part = 0.0;
+        for (long long i = (j + 1 > r0 ? j + 1 : r0) + tid; i < r1; i += kQrThreads) {
+            const double x = A[i * n + j];
+            part = fma(x, x, part);
+        }
+        part = warp_sum(part);
+        if (lane == 0) s_part[warp][0] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < nwarps; w++) t += s_part[w][0];
+            if (t != 0.0) atomicAdd(nrm + j, t);
+        }
+        grid_barrier(bar, epoch, n_cta);
+        const double xnorm = sqrt(__ldcg(nrm + j));
+        const double alpha = __ldcg(A + (long long)j * n + j);  // (the pivot is not overwritten: R is not needed)
+        double tau = 0.0, scale = 0.0;
+        if (xnorm != 0.0) {
+            const double beta = -copysign(hypot(alpha, xnorm), alpha);
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        if (blockIdx.x == 0 && tid == 0) taus[j] = tau;
+        if (tau != 0.0) {
+            // ---- w[c] = sum_i v_i A[i][c]; the column is scaled to the reflector on the way
+            column_products(j, j, scale, true, true, fwd + (long long)j * n);
+            grid_barrier(bar, epoch, n_cta);
+            if (tid < 64) s_tw[tid] = (j + 1 + tid < n) ? tau * __ldcg(fwd + (long long)j * n + j + 1 + tid) : 0.0;
+            __syncthreads();
+            const int c0 = j + 1 + lane, c1 = j + 33 + lane;
+            for (long long i = (j > r0 ? j : r0) + warp; i < r1; i += nwarps) {
+                const double v = (i == j) ? 1.0 : A[i * n + j];
+                if (c0 < n) A[i * n + c0] -= v * s_tw[lane];
+                if (c1 < n) A[i * n + c1] -= v * s_tw[32 + lane];
+            }
+            __syncthreads();
+        } else {
+            grid_barrier(bar, epoch, n_cta);  // keep the barrier count uniform
+        }
+    }
+    // ---- dorg2r: Q = H_0 ... H_{n-1} applied to the first n columns of I, built backwards
+    grid_barrier(bar, epoch, n_cta);
+    for (int j = n - 1; j >= 0; j--) {
+        const double tau = __ldcg(taus + j);
+        column_products(j, j + 1, 1.0, false, false, bwd + (long long)j * n);
+        grid_barrier(bar, epoch, n_cta);
+        if (tid < 64) s_tw[tid] = (j + 1 + tid < n) ? tau * __ldcg(bwd + (long long)j * n + j + 1 + tid) : 0.0;
+        __syncthreads();
+        const int c0 = j + 1 + lane, c1 = j + 33 + lane;
+        if (j >= r0 && j < r1 && warp == 0) {  // row j: 0 - 1 * tw
+            if (c0 < n) A[(long long)j * n + c0] = -s_tw[lane];
+            if (c1 < n) A[(long long)j * n + c1] = -s_tw[32 + lane];
+        }
+        for (long long i = (j + 1 > r0 ? j + 1 : r0) + warp; i < r1; i += nwarps) {
+            const double v = A[i * n + j];
+            if (c0 < n) A[i * n + c0] -= v * s_tw[lane];
+            if (c1 < n) A[i * n + c1] -= v * s_tw[32 + lane];
+        }
+        __syncthreads();
+        // column j itself: Q[:, j] = e_j - tau v
+        for (long long i = (j + 1 > r0 ? j + 1 : r0) + tid; i < r1; i += kQrThreads) A[i * n + j] *= -tau;
+        if (j >= r0 && j < r1 && tid == 0) A[(long long)j * n + j] = 1.0 - tau;
+        for (long long r = r0 + tid; r < j && r < r1; r += kQrThreads) A[r * n + j] = 0.0;
+        __syncthreads();
+    }
+}
+
 }  // namespace ttsk
 
 extern "C" int ttsk_pinv(ttsk_ctx* ctx, const double* d_A, int m, int n, double rcond, double* d_pinv, void* stream) {
@@ -237,6 +367,30 @@ extern "C" int ttsk_qr_q(ttsk_ctx* ctx, double* d_A, int64_t m, int n, void* str
     TTSK_ARG(ctx != nullptr, "ctx is NULL");
     TTSK_ARG(m >= n && n >= 1 && n <= 1024, "qr: need m >= n >= 1");
     TTSK_ARG(d_A != nullptr, "NULL pointer");
+    static const int one_cta = getenv("TTSK_QR_ONE_CTA") ? atoi(getenv("TTSK_QR_ONE_CTA")) : 0;
+    if (m >= 8192 && n <= 64 && !one_cta) {
+        // tall panel: every SM takes a block of rows, the Householder steps run in lock step (cooperative launch)
+        int per_sm = 0;
+        TTSK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ttsk::householder_q_grid_kernel, ttsk::kQrThreads, 0));
+        if (per_sm >= 1) {
+            long long grid = ctx->sm_count;
+            long long rows = (m + grid - 1) / grid;
+            if (rows < 256) rows = 256;
+            grid = (m + rows - 1) / rows;
+            const int64_t red_doubles = (int64_t)n + 2LL * n * n + n;
+            TTSK_TRY(ctx->ws_reserve(red_doubles * 8 + 1024));
+            ctx->ws_reset();
+            double* red = (double*)ctx->ws_alloc(red_doubles * 8 + 256);
+            unsigned* bar = (unsigned*)(red + red_doubles);
+            TTSK_CUDA(cudaMemsetAsync(red, 0, (size_t)red_doubles * 8 + 256, (cudaStream_t)stream));
+            long long m_arg = m;
+            void* args[] = {(void*)&d_A, (void*)&m_arg, (void*)&n, (void*)&rows, (void*)&red, (void*)&bar};
+            TTSK_CUDA(cudaLaunchCooperativeKernel((const void*)ttsk::householder_q_grid_kernel, dim3((unsigned)grid), dim3(ttsk::kQrThreads),
+                                                  args, 0, (cudaStream_t)stream));
+            ctx->launches++;
+            return TTSK_OK;
+        }
+    }
     TTSK_TRY(ctx->ws_reserve((int64_t)n * 8 + 1024));
     ctx->ws_reset();
     double* tau = (double*)ctx->ws_alloc((int64_t)n * 8);

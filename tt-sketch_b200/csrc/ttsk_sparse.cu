@@ -234,18 +234,23 @@ __global__ void __launch_bounds__(kPartThreads) partition_kernel(const long long
                                                                 int n_mu, const int* __restrict__ offs,
                                                                 const int* __restrict__ tstart, int* __restrict__ cursors,
                                                                 unsigned long long* __restrict__ out_words, long long block_len) {
-    __shared__ int s_cnt[kPartBins];
+    // every warp ranks its elements in its OWN row of counters (one address hit by all 16 warps serialises at the
+    // bank: the first sweep has only ~80 live digits); a prefix over the warps then places the rows of a digit
+    __shared__ int s_wcnt[kPartThreads / 32][kPartBins];
     __shared__ int s_base[kPartBins];
     __shared__ int s_cur[kPartBins];
+    __shared__ int s_tot[kPartBins];
+    __shared__ int s_loc[kPartBins];
+    __shared__ unsigned long long s_out[kPartTile];
     __shared__ long long s_range[2];
     __shared__ int s_bucket;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5;
     // LEVEL 1: tiles of this CTA's block; LEVEL 2: tiles of the whole array, strided over the grid
     const long long blk_lo = (long long)blockIdx.x * block_len, blk_hi = (blk_lo + block_len < n) ? blk_lo + block_len : n;
     const long long n_tiles = (LEVEL == 1) ? (blk_hi > blk_lo ? (blk_hi - blk_lo + kPartTile - 1) / kPartTile : 0) : (long long)tstart[kPartBins];
     if (LEVEL == 1 && tid < kPartBins) s_cur[tid] = cursors[blockIdx.x * kPartBins + tid];
     for (long long t = (LEVEL == 1) ? 0 : blockIdx.x; t < n_tiles; t += (LEVEL == 1) ? 1 : gridDim.x) {
-        if (tid < kPartBins) s_cnt[tid] = 0;
+        for (int i = tid; i < (kPartThreads / 32) * kPartBins; i += kPartThreads) (&s_wcnt[0][0])[i] = 0;
         if (tid == 0) {
             if (LEVEL == 1) {
                 s_range[0] = blk_lo + t * kPartTile;
@@ -283,27 +288,59 @@ __global__ void __launch_bounds__(kPartThreads) partition_kernel(const long long
             if (w[u] != ~0ull) {
                 const int key = (int)(w[u] >> 32);
                 const int dgt = (LEVEL == 1) ? (key >> 7) : (key & (kPartBins - 1));
-                rank[u] = atomicAdd(&s_cnt[dgt], 1);
+                rank[u] = atomicAdd(&s_wcnt[warp][dgt], 1);
             }
         }
         __syncthreads();
         if (tid < kPartBins) {
-            const int c = s_cnt[tid];
+            int total = 0;
+#pragma unroll
+            for (int ww = 0; ww < kPartThreads / 32; ww++) {
+                const int c = s_wcnt[ww][tid];
+                s_wcnt[ww][tid] = total;
+                total += c;
+            }
+            s_tot[tid] = total;
             if (LEVEL == 1) {
                 s_base[tid] = s_cur[tid];
-                s_cur[tid] += c;
-            } else if (c) {
-                s_base[tid] = atomicAdd(&cursors[s_bucket * kPartBins + tid], c);
+                s_cur[tid] += total;
+            } else if (total) {
+                s_base[tid] = atomicAdd(&cursors[s_bucket * kPartBins + tid], total);
             }
         }
         __syncthreads();
+        if (tid < 32) {  // exclusive scan of the 128 digit totals: where a digit's run starts inside the tile
+            int v[kPartBins / 32], run = 0;
+#pragma unroll
+            for (int k = 0; k < kPartBins / 32; k++) { v[k] = s_tot[4 * tid + k]; run += v[k]; }
+            int incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += y;
+            }
+            int excl = incl - run;
+#pragma unroll
+            for (int k = 0; k < kPartBins / 32; k++) { s_loc[4 * tid + k] = excl; excl += v[k]; }
+        }
+        __syncthreads();
+        // the tile in digit order in shared memory, then out in runs: consecutive threads write consecutive words of
+        // a run (a lane-per-element scatter costs one L2 sector write per word, the limit of these sweeps)
 #pragma unroll
         for (int u = 0; u < kPartPer; u++) {
             if (w[u] != ~0ull) {
                 const int key = (int)(w[u] >> 32);
                 const int dgt = (LEVEL == 1) ? (key >> 7) : (key & (kPartBins - 1));
-                out_words[s_base[dgt] + rank[u]] = w[u];
+                s_out[s_loc[dgt] + s_wcnt[warp][dgt] + rank[u]] = w[u];
             }
+        }
+        __syncthreads();
+        const int n_here = (int)(hi - lo);
+        for (int i = tid; i < n_here; i += kPartThreads) {
+            const unsigned long long x = s_out[i];
+            const int key = (int)(x >> 32);
+            const int dgt = (LEVEL == 1) ? (key >> 7) : (key & (kPartBins - 1));
+            out_words[s_base[dgt] + (i - s_loc[dgt])] = x;
         }
         __syncthreads();
     }

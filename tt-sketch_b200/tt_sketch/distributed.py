@@ -152,10 +152,12 @@ def check_same_drms(left_drm, right_drm, group=None) -> None:
 
 
 def distributed_stream_sketch(tensor: Tensor, left_drm, right_drm, group=None,
-                              local_sketch: Optional[Callable] = None) -> SketchContainer:
+                              local_sketch: Optional[Callable] = None, dst: Optional[int] = None) -> Optional[SketchContainer]:
     """Streaming sketch of `tensor` computed by all ranks of `group`; every rank returns the
-    full SketchContainer.  `local_sketch(part, left_drm, right_drm, total)` must return the packed
-    partial sketch as a torch tensor on the backend's device (default: this rank's GPU)."""
+    full SketchContainer -- or, with `dst` given, only that rank does (one NCCL reduce instead of an all-reduce and
+    ONE device->host copy of the packed sketch instead of one per rank: the ranks of a box share the host's
+    memory bandwidth); the others return None.  `local_sketch(part, left_drm, right_drm, total)` must return the
+    packed partial sketch as a torch tensor on the backend's device (default: this rank's GPU)."""
     import torch
     import torch.distributed as dist
 
@@ -175,7 +177,12 @@ def distributed_stream_sketch(tensor: Tensor, left_drm, right_drm, group=None,
     if packed.numel() != total:
         raise ValueError("local sketch has the wrong packed length")
     if world > 1:
-        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        if dst is None:
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.reduce(packed, dst=dst, op=dist.ReduceOp.SUM, group=group)
+            if rank != dst:
+                return None
     if packed.is_cuda:
         from tt_sketch import _backend as be
 
