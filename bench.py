@@ -263,7 +263,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL logs (its version banner at NCCL_DEBUG=WARN/INFO) stays off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     from ctypes import byref, c_double
 

@@ -173,7 +173,7 @@ def main(args):
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logging stays off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     import tt_sketch.drm as drm
     import tt_sketch.sketch as sketch

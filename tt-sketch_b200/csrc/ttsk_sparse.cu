@@ -846,7 +846,13 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
             if (which == 1) ctx->n_pass_events++;
             return TTSK_OK;
         };
-        if (mu == d - 1 && !has_x) {  // last mode: no bucketing needed when the mode fits shared memory
+        // last mode: no bucketing needed when the mode fits shared memory -- but the unbucketed form adds every
+        // generated entry into the CTA's T with a CAS loop (no native FP64 shared-memory atomic: ~1.7 ps per entry
+        // measured), the sorted form keeps per-column sums in registers and costs one bucketing (~12 ps per nonzero
+        // since the two-level partition): sorted wins from about 8 columns on
+        static const int last_env = getenv("TTSK_LAST_MODE_FLAT") ? atoi(getenv("TTSK_LAST_MODE_FLAT")) : -1;
+        const bool prefer_sorted = last_env >= 0 ? last_env == 0 : (P.rA >= 8 && nnz >= 65536 && shape[mu] <= 16384);
+        if (mu == d - 1 && !has_x && !prefer_sorted) {
             TTSK_TRY(mark(0));
             TTSK_TRY(try_launch_gw_flat(ctx, P, st, &flat_done));
             if (!flat_done) TTSK_TRY(launch_last_mode_unbucketed(ctx, P, st, &flat_done));

@@ -656,3 +656,4 @@ int try_launch_gw_seg(ttsk_ctx* ctx, PassParams& P, bool has_x, cudaStream_t st,
 }
 
 }  // namespace ttsk
+
