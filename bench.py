@@ -70,17 +70,23 @@ def make_coo(nnz, lo, hi):
     return idx, val
 
 
-def measured_traffic(nnz):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the pass kernel, per launch, from the committed
-    ncu --set full capture of this workload (profiles/r01_pass_traffic_1e8nnz.json); None for other sizes."""
-    path = os.path.join(ROOT, "profiles", "r01_pass_traffic_1e8nnz.json")  # rewritten by tools/ncu_summary.py
+def _pass_profile(nnz):
+    """Summary of the committed ncu --set full capture of this workload's mode-pass kernels
+    (profiles/r02_pass_traffic_1e8nnz.json, written by tools/ncu_summary.py); None for other sizes."""
+    path = os.path.join(ROOT, "profiles", "r02_pass_traffic_1e8nnz.json")
     try:
         d = json.load(open(path))
         if int(d["nnz"]) == int(nnz):
-            return float(d["dram_bytes_per_launch_avg"])
-    except Exception:
+            return d
+    except (OSError, ValueError, KeyError):
         pass
     return None
+
+
+def measured_traffic(nnz):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the pass kernels, per launch."""
+    d = _pass_profile(nnz)
+    return float(d["dram_bytes_per_launch_avg"]) if d else None
 
 
 def measured_hbm_peak():
@@ -262,8 +268,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
+    json_out = sys.stdout
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL logs (its version banner at NCCL_DEBUG=WARN/INFO) stays off stdout: one JSON line only
+        # one JSON line only on stdout: NCCL / torch print a version banner on fd 1 from native code, so fd 1 is
+        # pointed at stderr for the whole run and the line is written to a duplicate of the original stdout
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     from ctypes import byref, c_double
 
@@ -393,12 +404,12 @@ def main():
             "config": config_dict(nnz, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(nnz) if world == 1 else None, "peak_source": which,
-                         "kernel": "ttsk::sparse_pass_kernel / ttsk::sparse_sg_kernel (one launch per mode)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_NNZ * n_loc / n_pass,
+                         "kernel": "ttsk::gw_kernel (modes 0, 2, 3: fused lazy-Gaussian generator) / ttsk::sparse_pass_kernel (mode 1: table-row gather), one launch per mode", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_NNZ * n_loc / n_pass,
                          "launches_per_step": n_pass,
                          "note": "algorithmic 40 B/nnz over the d=4 mode passes (10 B/nnz per launch) / summed pass "
                                  "time of the last step; the kernel is FP64-issue-bound (bit-exact ndtri), see "
                                  "fp64_pipe and DESIGN.md section 3"},
-            "fp64_pipe": fp64_model(n_loc, pass_kernels_ms),
+            "fp64_pipe": fp64_model(n_loc, pass_kernels_ms, nnz),
             "kernel_ms": {"pass_kernels_last_step": pass_kernels_ms, "all_kernels_last_step": step_kernels_ms,
                           "per_pass_last_step": per_pass_ms},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -408,25 +419,30 @@ def main():
         if world == 1 and not args.no_cpu:
             ref = cpu_baseline_subprocess(["--ref-nnz", str(args.cpu_nnz)])
             out["cpu_baseline"] = dict(ref["cpu_baseline"], ms=ref["ms_per_step"])
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def fp64_model(n_loc, pass_ms):
-    """FP64-pipe view of the same kernel: FP64 instructions the algorithm needs per nonzero
-     over the measured DFMA issue rate of this B200 (tools/fp64_microbench)."""
-    otf_variates = 20 + 20 + 40            # L_1, L_2, R_0 (L_0, R_1, R_2 come from prefix tables)
-    per_variate = 0.73 * 42 + 0.27 * 112   # central / tail branch FP64 instructions
-    # Psi_0 and Psi_1 as padded 8x8x4 MMA tiles, Psi_3 likewise; Psi_2 / Omega_1 run in the segment-GEMM form:
-    # 20 multiplies + 20 adds per nonzero (the per-segment GEMMs are negligible)
-    mma_fma = 8 * 40 + 24 * 40 + 24 * 8 + 2 * 20
-    per_nnz = otf_variates * per_variate + mma_fma
-    peak = 1.68e13
+# FP64-pipe peak of this pool's B200 on the generator's instruction mix (unfused DMUL + DADD chains), thread
+# instructions per second: tools/fp64_mix_microbench (profiles/r02_fp64_mix_microbench.txt); plain DFMA: 1.70e13
+FP64_PIPE_PEAK = 1.85e13
+
+
+def fp64_model(n_loc, pass_ms, nnz_total):
+    """FP64-pipe view of the same kernels: FP64-pipe instructions per nonzero MEASURED by ncu
+    (smsp__inst_executed_pipe_fp64.sum of the four pass launches, profiles/r02_pass_traffic_1e8nnz.json; the
+    instruction count per nonzero does not depend on the shard size) over the measured issue rate of the pipe."""
+    d = _pass_profile(nnz_total)
+    if d and d.get("fp64_pipe_thread_instructions_per_nnz"):
+        per_nnz, src = float(d["fp64_pipe_thread_instructions_per_nnz"]), "ncu smsp__inst_executed_pipe_fp64.sum x 32 / nnz (profiles/r02_pass_traffic_1e8nnz.json)"
+    else:  # other sizes: 80 on-the-fly variates x (0.73 x 38 central + 0.27 x 140 tail incl. the discarded central evaluation) + accumulation
+        per_nnz, src = 80 * (0.73 * 38 + 0.27 * 140) + 1400.0, "model (no ncu capture at this size)"
     ach = per_nnz * n_loc / (pass_ms * 1e-3) if pass_ms > 0 else 0.0
-    return {"fp64_instr_per_nnz_model": per_nnz, "achieved_instr_per_s": ach, "peak_instr_per_s": peak,
-            "frac": ach / peak, "peak_source": "measured DFMA issue rate, tools/fp64_microbench on this pool's B200"}
+    return {"fp64_instr_per_nnz": per_nnz, "fp64_instr_per_nnz_source": src, "achieved_instr_per_s": ach,
+            "peak_instr_per_s": FP64_PIPE_PEAK, "frac": ach / FP64_PIPE_PEAK,
+            "peak_source": "measured DMUL+DADD issue rate, tools/fp64_mix_microbench on this pool's B200 (1.85e13 thread-instr/s)"}
 
 
 if __name__ == "__main__":

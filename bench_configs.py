@@ -172,8 +172,11 @@ def main(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
+    json_out = sys.stdout
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logging stays off stdout (one JSON line only)
+        sys.stdout.flush()  # one JSON line only on stdout: native banners (NCCL) go to stderr, see bench.py
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     import tt_sketch.drm as drm
     import tt_sketch.sketch as sketch
@@ -275,7 +278,7 @@ def main(args):
         if world == 1 and not args.no_cpu:
             ref = cpu_baseline_subprocess(["--config", cfg])
             res["cpu_baseline"] = dict(ref["cpu_baseline"], ms=ref["ms_per_step"])
-        print(json.dumps(res), flush=True)
+        print(json.dumps(res), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -2,7 +2,7 @@
 """Summarise an `ncu --set full` report of the mode-pass kernels into profiles/:
     python tools/ncu_summary.py gpurun_out/X.ncu-rep NNZ TAG
 writes profiles/TAG_ncu_full_pass_kernels.csv (selected raw metrics per launch) and
-profiles/r01_pass_traffic_1e8nnz.json (DRAM bytes per launch, read by bench.py)."""
+profiles/r02_pass_traffic_1e8nnz.json (DRAM bytes and FP64-pipe instructions per launch, read by bench.py)."""
 import csv
 import io
 import json
@@ -18,7 +18,8 @@ hdr, units, data = rows[0], rows[1], rows[2:]
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "smsp__issue_active.avg.per_cycle_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
+        "smsp__issue_active.avg.per_cycle_active", "smsp__inst_executed.sum", "smsp__inst_executed_pipe_fp64.sum",
+        "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "smsp__warps_active.avg.per_cycle_active",
         "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
@@ -44,12 +45,18 @@ def scale(v, u):
 
 kn, ti = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
 ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+fi = hdr.index("smsp__inst_executed_pipe_fp64.sum") if "smsp__inst_executed_pipe_fp64.sum" in hdr else None
+ai = hdr.index("smsp__inst_executed.sum")
 kernels = []
 for r in data:
     kernels.append({"kernel": r[kn], "ms": float(r[ti]) * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(units[ti], 1.0),
-                    "dram_bytes": scale(r[ri], units[ri]) + scale(r[wi], units[wi])})
+                    "dram_bytes": scale(r[ri], units[ri]) + scale(r[wi], units[wi]),
+                    "warp_instructions": float(r[ai]),
+                    "fp64_pipe_warp_instructions": float(r[fi]) if fi is not None else None})
 tot = sum(k["dram_bytes"] for k in kernels)
+fp64 = sum(k["fp64_pipe_warp_instructions"] or 0.0 for k in kernels)
 json.dump({"nnz": nnz, "source": f"ncu --set full, profiles/{os.path.basename(out)}", "kernels": kernels,
-           "dram_bytes_all_pass_launches": tot, "dram_bytes_per_launch_avg": tot / max(1, len(kernels))},
-          open(os.path.join(ROOT, "profiles", "r01_pass_traffic_1e8nnz.json"), "w"), indent=1)
+           "dram_bytes_all_pass_launches": tot, "dram_bytes_per_launch_avg": tot / max(1, len(kernels)),
+           "fp64_pipe_thread_instructions_per_nnz": 32.0 * fp64 / nnz},
+          open(os.path.join(ROOT, "profiles", "r02_pass_traffic_1e8nnz.json"), "w"), indent=1)
 print(out, len(kernels), "launches", tot / 1e9, "GB")

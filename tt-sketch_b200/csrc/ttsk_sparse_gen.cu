@@ -82,43 +82,65 @@ __device__ __forceinline__ void gw_hash(unsigned long long flat, unsigned salt_a
     }
 }
 
-// central branch of IL columns -> store; tails keep b = 1 + u in the slot and are queued (slot address >> 3).
-// `slot0` -> this lane's slot of the first column.  One predicate per variate drives the select, the ballot and the
-// queue push (written in PTX: the compiler otherwise materialises the predicate twice).
+// Classify IL hashed columns and queue them.  Every element stores b = 1 + u (the uniform with the exponent of 1.0) in
+// its slot and pushes the slot (address >> 3, 16 bits) on one of the warp's two queues, which share one array of
+// r * 32 entries: elements that are surely in the central branch of ndtri grow a queue from the front, elements
+// whose high word says they MAY be in a tail grow one from the back.  Both branches are then evaluated densely --
+// no lane computes a central branch whose result a tail would overwrite (27 % of the lanes did before).
+// `cq_lane` = central front + 2 * lane (per lane), `tq` = tail back (warp-uniform).  One predicate per variate.
 template <int IL>
-__device__ __forceinline__ void gw_central(const unsigned (&hi)[IL], const unsigned (&lo)[IL], double (&cc)[IL]) {
-#pragma unroll
-    for (int c = 0; c < IL; c++) cc[c] = ndtri_central_b(__hiloint2double((int)(hi[c] | 0x3FF00000u), (int)lo[c]));
-}
-template <int IL>
-__device__ __forceinline__ void gw_store(const unsigned (&hi)[IL], const unsigned (&lo)[IL], const double (&cc)[IL], unsigned slot0,
-                                         unsigned& wq_top, unsigned lt) {
+__device__ __forceinline__ void gw_classify(const unsigned (&hi)[IL], const unsigned (&lo)[IL], unsigned slot0, unsigned& cq_lane,
+                                            unsigned& tq, unsigned lt) {
     const unsigned e0 = slot0 >> 3;
 #pragma unroll
     for (int c = 0; c < IL; c++) {
-        const unsigned bh = hi[c] | 0x3FF00000u;  // high word of b; the tail test runs on it (no separate mask)
+        const unsigned bh = hi[c] | 0x3FF00000u;
         const double b = __hiloint2double((int)bh, (int)lo[c]);
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            ".reg .b32 m, t, q;\n"
-            "sub.u32 t, %1, %2;\n"
-            "setp.ge.u32 p, t, %3;\n"
+            ".reg .b32 m, t, n2, c2, at, ac;\n"
+            "sub.u32 t, %2, %3;\n"
+            "setp.ge.u32 p, t, %4;\n"            // may be a tail
             "st.shared.f64 [%6], %5;\n"
-            "@p st.shared.f64 [%6], %4;\n"
             "vote.sync.ballot.b32 m, p, 0xffffffff;\n"
-            "popc.b32 q, m;\n"
-            "@p and.b32 t, m, %7;\n"
-            "@p popc.b32 t, t;\n"
-            "@p mad.lo.u32 t, t, 2, %0;\n"
-            "@p st.shared.u16 [t], %8;\n"
-            "mad.lo.u32 %0, q, 2, %0;\n"
+            "popc.b32 n2, m;\n"
+            "shl.b32 n2, n2, 1;\n"
+            "and.b32 c2, m, %7;\n"
+            "popc.b32 c2, c2;\n"
+            "shl.b32 c2, c2, 1;\n"               // 2 * (tails before this lane)
+            "sub.u32 %1, %1, n2;\n"              // the tail queue grows down by the step's tails
+            "add.u32 at, %1, c2;\n"
+            "sub.u32 ac, %0, c2;\n"              // central slot: front + 2 * (lane - tails before this lane)
+            "selp.u32 at, at, ac, p;\n"
+            "st.shared.u16 [at], %8;\n"
+            "add.u32 %0, %0, 64;\n"
+            "sub.u32 %0, %0, n2;\n"              // the central queue grows by 32 - tails
             "}"
-            : "+r"(wq_top)
-            : "r"(bh), "n"(kCentralLo + 0x3FF00000u), "n"(kCentralSpan), "d"(b), "d"(cc[c]), "r"(slot0 + (unsigned)(kGwPB * 8 * c)), "r"(lt),
+            : "+r"(cq_lane), "+r"(tq)
+            : "r"(bh), "n"(kCentralLo + 0x3FF00000u), "n"(kCentralSpan), "d"(b), "r"(slot0 + (unsigned)(kGwPB * 8 * c)), "r"(lt),
               "h"((unsigned short)(e0 + (unsigned)(kGwPB * c)))
             : "memory");
     }
+}
+
+// central branch of the queue entries [q0, q0 + 32 IL), IL per lane in flight; a lane without a further entry repeats
+// its first one (same value written twice)
+template <int IL>
+__device__ __forceinline__ void gw_drain_central(unsigned q_addr, int q0, int count, int lane) {
+    const int qi = q0 + lane;
+    if (qi >= count) return;
+    unsigned a[IL];
+    double cc[IL];
+#pragma unroll
+    for (int c = 0; c < IL; c++) {
+        const int qc = (qi + 32 * c < count) ? qi + 32 * c : qi;
+        a[c] = ld_shared_u16(q_addr + 2u * qc) << 3;
+    }
+#pragma unroll
+    for (int c = 0; c < IL; c++) cc[c] = ndtri_central_b(ld_shared_f64(a[c]));
+#pragma unroll
+    for (int c = 0; c < IL; c++) st_shared_f64(a[c], cc[c]);
 }
 
 // the warp's deferred tails [q0, q0 + 32 IL) of its queue, IL entries per lane in flight (one entry alone is a chain of
@@ -149,51 +171,43 @@ __device__ __forceinline__ void gw_drain(unsigned wq_base, int q0, int wcount, u
     }
 }
 
-// the (r x 32) block of one tile: column `col` of lane's row at buf_lane + col * kGwPB * 8.  The hash of the next
-// group of columns is issued next to the central branch of the current one (independent instruction streams in one
-// basic block).  Measured on B200: an FP64 instruction costs two issue cycles and every other instruction one, with
-// no overlap in this mix however the two streams are interleaved (forcing a fine interleave through data
-// dependences changed nothing), so what counts is the number of non-FP64 instructions per variate.
+// the (r x 32) block of one tile: column `col` of lane's row at buf_lane + col * kGwPB * 8.  Three dense phases:
+// hash + classify every element, central branch over the front queue, tail branch over the back queue.  (Measured on
+// B200: an FP64 instruction costs two issue cycles and every other instruction one, with no overlap in this mix
+// however the streams are interleaved, so what counts is the number of instructions per variate -- and that no
+// lane evaluates a branch it will not keep.)
 __device__ __forceinline__ void gw_generate(unsigned long long flat, unsigned salt_base, int r, unsigned buf_lane,
                                             unsigned wq_base, unsigned lt, unsigned tab_addr, int lane) {
-    unsigned wq_top = wq_base;
     constexpr unsigned kColB = (unsigned)(kGwPB * 8);
-    const int groups = r / kGwIL;
+    const unsigned wq_end = wq_base + 64u * (unsigned)r;  // r * 32 entries of two bytes
+    unsigned cq_lane = wq_base + 2u * (unsigned)lane, tq = wq_end;
     int col = 0;
-    if (groups > 0) {
-        unsigned hi[kGwIL], lo[kGwIL];
-        gw_hash<kGwIL>(flat, salt_base, hi, lo);
 #pragma unroll 1
-        for (int g = 0; g + 1 < groups; g++, col += kGwIL) {
-            unsigned hn[kGwIL], ln[kGwIL];
-            double cc[kGwIL];
-            gw_central<kGwIL>(hi, lo, cc);
-            gw_hash<kGwIL>(flat, salt_base + 8u * (col + kGwIL), hn, ln);
-            gw_store<kGwIL>(hi, lo, cc, buf_lane + kColB * col, wq_top, lt);
-#pragma unroll
-            for (int c = 0; c < kGwIL; c++) { hi[c] = hn[c]; lo[c] = ln[c]; }
-        }
-        double cc[kGwIL];
-        gw_central<kGwIL>(hi, lo, cc);
-        gw_store<kGwIL>(hi, lo, cc, buf_lane + kColB * col, wq_top, lt);
-        col += kGwIL;
+    for (; col + kGwIL <= r; col += kGwIL) {
+        unsigned hi[kGwIL], lo[kGwIL];
+        gw_hash<kGwIL>(flat, salt_base + 8u * col, hi, lo);
+        gw_classify<kGwIL>(hi, lo, buf_lane + kColB * col, cq_lane, tq, lt);
     }
 #pragma unroll 1
     for (; col < r; col++) {
         unsigned hi[1], lo[1];
-        double cc[1];
         gw_hash<1>(flat, salt_base + 8u * col, hi, lo);
-        gw_central<1>(hi, lo, cc);
-        gw_store<1>(hi, lo, cc, buf_lane + kColB * col, wq_top, lt);
+        gw_classify<1>(hi, lo, buf_lane + kColB * col, cq_lane, tq, lt);
     }
     __syncwarp();
-    // deferred tails, dense over the queue: four entries per lane while that keeps most lanes busy, then two, then one
-    const int wcount = (int)((wq_top - wq_base) >> 1);
+    const int n_central = (int)((cq_lane - 2u * (unsigned)lane - wq_base) >> 1);
+    const int n_tail = (int)((wq_end - tq) >> 1);
     int q0 = 0;
 #pragma unroll 1
-    for (; wcount - q0 > 64; q0 += 32 * kGwTailIL) gw_drain<kGwTailIL>(wq_base, q0, wcount, tab_addr, lane);
-    if (wcount - q0 > 32) gw_drain<2>(wq_base, q0, wcount, tab_addr, lane);
-    else if (wcount - q0 > 0) gw_drain<1>(wq_base, q0, wcount, tab_addr, lane);
+    for (; n_central - q0 > 64; q0 += 32 * kGwIL) gw_drain_central<kGwIL>(wq_base, q0, n_central, lane);
+    if (n_central - q0 > 32) gw_drain_central<2>(wq_base, q0, n_central, lane);
+    else if (n_central - q0 > 0) gw_drain_central<1>(wq_base, q0, n_central, lane);
+    // deferred tails, dense over the back queue: four entries per lane while that keeps most lanes busy, then two, one
+    q0 = 0;
+#pragma unroll 1
+    for (; n_tail - q0 > 64; q0 += 32 * kGwTailIL) gw_drain<kGwTailIL>(tq, q0, n_tail, tab_addr, lane);
+    if (n_tail - q0 > 32) gw_drain<2>(tq, q0, n_tail, tab_addr, lane);
+    else if (n_tail - q0 > 0) gw_drain<1>(tq, q0, n_tail, tab_addr, lane);
     __syncwarp();
 }
 
