@@ -276,6 +276,84 @@ def gen_sparse_sign():
     print("sparse_sign.npz:", n, "cases")
 
 
+def gen_tucker_dense_gauss():
+    """Section 8(f) rank 2: TuckerTensor input under TT-DRMs (tucker_sketch.py:9-46, tensor_train_drm.py:124-145 of
+    the reference) and the DenseGaussianDRM (dense_gaussian_drm.py:17-80) on sparse / TT / dense inputs, incl. a
+    blocked sketch and a rank increase.  Stored like sketches.npz plus the DenseGaussianDRM matrices themselves."""
+    from tt_sketch.drm import DenseGaussianDRM
+    from tt_sketch.sketch_dispatch import get_sketch_method
+    from tt_sketch.tensor import TuckerTensor
+
+    store, names = {}, []
+    # ---- Tucker, d = 2, 3, 4 (the reference tests d = 2, 3 through exact recovery only)
+    for name, shape, trank, lrank, rrank in [("tucker_d2", (10, 11), 3, (3,), (4,)),
+                                             ("tucker_d3", (10, 11, 12), (3, 2, 4), (3, 4), (4, 5)),
+                                             ("tucker_d4", (7, 8, 9, 10), (3, 4, 2, 3), (3, 4, 5), (5, 6, 7))]:
+        X = TuckerTensor.random(shape, trank, seed=180)
+        left = TensorTrainDRM(lrank, shape=shape, transpose=False, seed=11)
+        right = TensorTrainDRM(rrank, shape=shape, transpose=True, seed=23)
+        store[name + "_core"] = X.core
+        for i, U in enumerate(X.factors):
+            store[name + f"_U{i}"] = U
+        drm_pack(name + "_L", left, store)
+        drm_pack(name + "_R", right, store)
+        store[name + "_lrank"] = np.array(lrank, dtype=np.int64)
+        store[name + "_rrank"] = np.array(rrank, dtype=np.int64)
+        stt = stream_sketch(X, lrank, rrank, left_drm=left, right_drm=right)
+        sketch_pack(name + "_stream", stt.Psi_cores, stt.Omega_mats, store)
+        for i, c in enumerate(stt.C_cores()):
+            store[name + f"_stream_C{i}"] = c
+        for i, m in enumerate(get_sketch_method(X, left)(X)):
+            store[name + f"_Lc{i}"] = np.ascontiguousarray(m)
+        for i, m in enumerate(get_sketch_method(X, right)(X)):
+            store[name + f"_Rc{i}"] = np.ascontiguousarray(m)
+        for i, c in enumerate(orthogonal_sketch(X, lrank, rrank, left_drm=left, right_drm=right).cores):
+            store[name + f"_orth_C{i}"] = c
+        for i, c in enumerate(hmt_sketch(X, rrank, drm=right).cores):
+            store[name + f"_hmt_C{i}"] = c
+        store[name + "_dense"] = X.to_numpy()
+        names.append(name)
+    store["tucker_names"] = np.array(names)
+    # ---- DenseGaussianDRM
+    shape = (5, 6, 7, 4)
+    lrank, rrank = (3, 4, 3), (4, 6, 4)
+    sp = make_sparse(shape, 200, 12)
+    tt = TensorTrain.random(shape, (3, 4, 2), seed=13)
+    dn = DenseTensor(np.random.default_rng(14).standard_normal(shape))
+    tensor_pack("dg_sparse_T", sp, store)
+    tensor_pack("dg_tt_T", tt, store)
+    tensor_pack("dg_dense_T", dn, store)
+    left = DenseGaussianDRM(lrank, shape=shape, transpose=False, seed=11)
+    right = DenseGaussianDRM(rrank, shape=shape, transpose=True, seed=23)
+    for side, drm in (("L", left), ("R", right)):
+        for i, m in enumerate(drm.sketching_mats):
+            store[f"dg_{side}_mat{i}"] = m
+    sl = DenseGaussianDRM(lrank, shape=shape, transpose=False, seed=11).slice((1, 1, 0), (3, 3, 2))
+    for i, m in enumerate(sl.sketching_mats):
+        store[f"dg_Lslice_mat{i}"] = m
+    inc = left.increase_rank((4, 5, 4))
+    for i, m in enumerate(inc.sketching_mats):
+        store[f"dg_Linc_mat{i}"] = m
+    for key, X in (("dg_sparse", sp), ("dg_tt", tt), ("dg_dense", dn)):
+        stt = stream_sketch(X, lrank, rrank, left_drm=left, right_drm=right)
+        sketch_pack(key + "_stream", stt.Psi_cores, stt.Omega_mats, store)
+        for i, m in enumerate(get_sketch_method(X, left)(X)):
+            store[key + f"_Lc{i}"] = np.ascontiguousarray(m)
+        for i, m in enumerate(get_sketch_method(X, right)(X)):
+            store[key + f"_Rc{i}"] = np.ascontiguousarray(m)
+        for i, c in enumerate(orthogonal_sketch(X, lrank, rrank, left_drm=left, right_drm=right).cores):
+            store[key + f"_orth_C{i}"] = c
+    lsl, rsl = [(0, 0, 0), (2, 2, 1), (3, 4, 3)], [(0, 0, 0), (2, 3, 2), (4, 6, 4)]
+    sk = blocked_stream_sketch(sp, left, right, lsl, rsl)
+    sketch_pack("dg_sparse_blocked", sk.Psi_cores, sk.Omega_mats, store)
+    store["dg_lslices"] = np.array(lsl, dtype=np.int64)
+    store["dg_rslices"] = np.array(rsl, dtype=np.int64)
+    store["dg_lrank"] = np.array(lrank, dtype=np.int64)
+    store["dg_rrank"] = np.array(rrank, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "tucker_dense_gauss.npz"), **store)
+    print("tucker_dense_gauss.npz:", names)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "stt_ops":  # later additions leave the earlier fixtures untouched
         gen_stt_ops()
@@ -283,11 +361,15 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "sparse_sign":
         gen_sparse_sign()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "tucker_dense_gauss":
+        gen_tucker_dense_gauss()
+        sys.exit(0)
     gen_lazy_gaussian()
     gen_sketches()
     gen_ttdrm_cores()
     gen_stt_ops()
     gen_sparse_sign()
+    gen_tucker_dense_gauss()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")

@@ -53,7 +53,7 @@ def test_linearity_and_split_full_size_stream():
 def test_host_streaming_call_equals_device_call():
     """ttsk_sparse_sketch_host (graduated chunks through pinned staging: every chunk buckets, passes and flushes its
     own segments) == ttsk_sparse_sketch on device-resident COO: two different tilings of the same sums, including
-    the segment-GEMM and the unbucketed last-mode forms (shape (3000, 3000, 40, 50), 3e6 nonzeros -> chunks of 1e6 and 2e6)."""
+    the segment-GEMM form (shape (3000, 3000, 40, 50), 3e6 nonzeros -> chunks of 1e6 and 2e6)."""
     import torch
     from ctypes import byref
     from tt_sketch import _backend as be
@@ -76,12 +76,35 @@ def test_host_streaming_call_equals_device_call():
     be.check(lib.ttsk_sparse_sketch(ctx, 4, be.as_i64(shape), nnz, be.ptr(d_idx), d_idx.stride(0), be.ptr(d_val),
                                     byref(ld), byref(rd), be.ptr(out), 0, be.stream()))
     torch.cuda.synchronize()
-    assert lib.ttsk_sg_pass_count(ctx) >= sg0 + 2, "segment-GEMM / unbucketed forms were not taken"
+    assert lib.ttsk_sg_pass_count(ctx) >= sg0 + 1, "the segment-GEMM form was not taken"
     h_idx, h_val = torch.from_numpy(X.indices).pin_memory(), torch.from_numpy(X.entries).pin_memory()
     h_out = torch.empty(total, dtype=torch.float64).pin_memory()
     be.check(lib.ttsk_sparse_sketch_host(ctx, 4, be.as_i64(shape), nnz, h_idx.data_ptr(), h_idx.stride(0),
                                          h_val.data_ptr(), byref(ld), byref(rd), h_out.data_ptr(), 0))
     assert _close(h_out.numpy(), out.cpu().numpy(), tol=1e-11)
+
+
+def test_unbucketed_last_mode_vs_oracle(oracle_lib):
+    """Narrow left rank (4 columns): the last mode takes the unbucketed form (T[i_mu, :] in shared memory, CAS adds),
+    wide ranks take the sorted register-accumulating form; both against the CPU oracle at 1e5 nonzeros."""
+    from tt_sketch import _backend as be
+    from tt_sketch.drm import SparseGaussianDRM
+    from tt_sketch.sketch import stream_sketch
+
+    shape = (300, 300, 40, 50)
+    nnz = 100_000
+    X = _sparse(shape, nnz, 21)
+    for lr, rr, flat in [((4, 4, 4), (6, 6, 6), True), ((12, 12, 12), (16, 16, 16), False)]:
+        L, R = _drms(shape, lr, rr, SparseGaussianDRM, SparseGaussianDRM)
+        sg0 = be.lib().ttsk_sg_pass_count(be.ctx())
+        stt = stream_sketch(X, lr, rr, left_drm=L, right_drm=R)
+        taken = be.lib().ttsk_sg_pass_count(be.ctx()) - sg0
+        oL = oracle_lib.Drm("gauss", False, shape, (0,) * 3, lr, int(L.seed))
+        oR = oracle_lib.Drm("gauss", True, shape, (0,) * 3, rr, int(R.seed))
+        Psi, Om = oracle_lib.general_sketch(("sparse", shape, X.indices, X.entries), oL, oR, "streaming", fast_sparse=True)
+        for a, b in zip(stt.Psi_cores + stt.Omega_mats, Psi + Om):
+            assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+        assert (taken >= 1) if flat else True
 
 
 @pytest.mark.parametrize("kind", ["gauss", "tt"])
@@ -167,3 +190,101 @@ def test_errors_raise_like_reference():
     tt = TensorTrain.random((5, 6, 7), 2, seed=1)
     with pytest.raises(AttributeError):  # Gaussian DRM cannot sketch a TT (capability missing)
         stream_sketch(tt, (2, 3), (3, 4), left_drm=L2, right_drm=R)
+
+
+def test_tt_gather_and_sampled_error_on_device():
+    """TensorTrain.gather (reference tensor.py:414-440) through the per-nonzero chain kernel == entries of the dense
+    reconstruction; SparseTensor.dot / error(fast=True) against a TT (tensor.py:250-255, 52-87) == dense arithmetic;
+    and at a size that cannot be densified (C4 shape, 2e6 nonzeros) the gather is linear in the TT."""
+    from tt_sketch.tensor import CPTensor, SparseTensor, TensorTrain
+
+    rng = np.random.default_rng(0)
+    shape = (6, 7, 8, 5)
+    tt = TensorTrain.random(shape, (3, 4, 2), seed=5)
+    idx = np.stack([rng.integers(0, n, 500) for n in shape]).astype(np.int64)
+    dense = tt.to_numpy()
+    assert np.max(np.abs(tt.gather(idx) - dense[tuple(idx)])) <= 1e-14 * np.max(np.abs(dense))
+    assert np.max(np.abs(tt.gather(tuple(idx)) - dense[tuple(idx)])) <= 1e-14 * np.max(np.abs(dense))
+    flat = rng.choice(int(np.prod(shape)), 300, replace=False)
+    uidx = np.stack(np.unravel_index(flat, shape)).astype(np.int64)
+    sp = SparseTensor(shape, uidx, rng.standard_normal(300))
+    assert abs(sp.dot(tt) - float(np.sum(sp.to_numpy() * dense))) <= 1e-12 * max(1.0, abs(sp.dot(tt)))
+    exact = float(np.linalg.norm(sp.to_numpy() - dense))
+    assert abs(sp.error(tt, fast=True) - exact) <= 1e-7 * exact
+    assert abs(sp.error(tt) - exact) <= 1e-12 * exact
+    cp = CPTensor.random(shape, 3, seed=8)
+    assert abs(sp.dot(cp) - float(np.sum(sp.to_numpy() * cp.to_numpy()))) <= 1e-12
+    big = (10000, 10000, 10000, 500)
+    X = _sparse(big, 2_000_000, 31)
+    a, b = TensorTrain.random(big, 5, seed=1), TensorTrain.random(big, 3, seed=2)
+    ga, gb = a.gather(X.indices), b.gather(X.indices)
+    # the TT of the sum (block-diagonal cores) gathers to the sum of the gathers
+    cat = [np.concatenate([a.cores[0], b.cores[0]], axis=2)]
+    for ca, cb in zip(a.cores[1:-1], b.cores[1:-1]):
+        blk = np.zeros((ca.shape[0] + cb.shape[0], ca.shape[1], ca.shape[2] + cb.shape[2]))
+        blk[:ca.shape[0], :, :ca.shape[2]] = ca
+        blk[ca.shape[0]:, :, ca.shape[2]:] = cb
+        cat.append(blk)
+    cat.append(np.concatenate([a.cores[-1], b.cores[-1]], axis=0))
+    gs = TensorTrain(cat).gather(X.indices)
+    assert np.max(np.abs(gs - (ga + gb))) <= 1e-12 * np.max(np.abs(ga + gb))
+
+
+def test_public_operator_registry_is_the_plug_in_point():
+    """Replacing an entry of OMEGA_METHODS / PSI_METHODS (the reference's plug-in point, sketch_dispatch.py:59-82)
+    changes what stream_sketch / orthogonal_sketch run; restoring it restores the device path; a new tensor class
+    registered with NumPy-level operators and a host-only DRM method is sketched too."""
+    from tt_sketch import sketch_dispatch as sd
+    from tt_sketch.drm import TensorTrainDRM
+    from tt_sketch.sketch import orthogonal_sketch, stream_sketch
+    from tt_sketch.tensor import DenseTensor
+
+    shape = (5, 6, 7)
+    X = DenseTensor(np.random.default_rng(3).standard_normal(shape))
+    lr, rr = (3, 4), (4, 5)
+    L = TensorTrainDRM(lr, shape=shape, transpose=False, seed=1)
+    R = TensorTrainDRM(rr, shape=shape, transpose=True, seed=2)
+    base = stream_sketch(X, lr, rr, left_drm=L, right_drm=R)
+    calls = {"omega": 0, "psi": 0}
+    stock_o, stock_p = sd.OMEGA_METHODS[DenseTensor], sd.PSI_METHODS[DenseTensor]
+
+    def my_omega(left, right, **kw):
+        calls["omega"] += 1
+        return 2.0 * stock_o(left, right, **kw)
+
+    def my_psi(left, right, **kw):
+        calls["psi"] += 1
+        return 2.0 * stock_p(left, right, **kw)
+
+    sd.OMEGA_METHODS[DenseTensor], sd.PSI_METHODS[DenseTensor] = my_omega, my_psi
+    try:
+        doubled = stream_sketch(X, lr, rr, left_drm=L, right_drm=R)
+        orthogonal_sketch(X, lr, rr, left_drm=L, right_drm=R)
+    finally:
+        sd.OMEGA_METHODS[DenseTensor], sd.PSI_METHODS[DenseTensor] = stock_o, stock_p
+    assert calls == {"omega": 4, "psi": 6}
+    for a, b in zip(doubled.Psi_cores + doubled.Omega_mats, base.Psi_cores + base.Omega_mats):
+        assert _close(a, 2.0 * b, tol=1e-12)
+    again = stream_sketch(X, lr, rr, left_drm=L, right_drm=R)
+    for a, b in zip(again.Psi_cores + again.Omega_mats, base.Psi_cores + base.Omega_mats):
+        assert np.array_equal(a, b)
+
+    class Shifted(DenseTensor):  # a user-defined format: X + c, sketched through NumPy-level operators
+        pass
+
+    class MyDRM(TensorTrainDRM):
+        def sketch_shifted(self, tensor):  # host-only contraction, no *_device twin
+            return self.sketch_dense(DenseTensor(tensor.data))
+
+    sd.DRM_SKETCH_METHOD_DISPATCH[Shifted] = "sketch_shifted"
+    sd.OMEGA_METHODS[Shifted] = lambda l, r, *, tensor, **kw: stock_o(l, r, tensor=DenseTensor(tensor.data), **kw)
+    sd.PSI_METHODS[Shifted] = lambda l, r, *, tensor, **kw: stock_p(l, r, tensor=DenseTensor(tensor.data), **kw)
+    try:
+        ML = MyDRM(lr, shape=shape, transpose=False, seed=1)
+        MR = MyDRM(rr, shape=shape, transpose=True, seed=2)
+        got = stream_sketch(Shifted(X.data), lr, rr, left_drm=ML, right_drm=MR)
+    finally:
+        for reg in (sd.DRM_SKETCH_METHOD_DISPATCH, sd.OMEGA_METHODS, sd.PSI_METHODS):
+            reg.pop(Shifted, None)
+    for a, b in zip(got.Psi_cores + got.Omega_mats, base.Psi_cores + base.Omega_mats):
+        assert _close(a, b, tol=1e-12)

@@ -175,3 +175,71 @@ def test_fused_path_selection_is_host_logic_only():
     assert not _fusable(tt, tl, tr)
     big = TensorTrainDRM((70, 70), shape=(80, 80, 80), transpose=False, seed=1)
     assert not _fusable(SparseTensor((80, 80, 80), np.zeros((3, 1), dtype=np.int64), np.ones(1)), big, big)  # rank > 64
+
+
+def test_tensor_dot_norm_error_semantics_on_host():
+    """Tensor.dot / norm / error(fast) and the gathers that need no device (reference tensor.py:52-131, 250-291,
+    542-560, 670-671, 726-732) against dense NumPy arithmetic."""
+    from tt_sketch.tensor import CPTensor, DenseTensor, SparseTensor, TensorTrain
+
+    rng = np.random.default_rng(4)
+    shape = (5, 6, 7)
+    tt, tt2 = TensorTrain.random(shape, 3, seed=1), TensorTrain.random(shape, 2, seed=2)
+    cp = CPTensor.random(shape, 4, seed=3)
+    dn = DenseTensor(rng.standard_normal(shape))
+    assert abs(tt.dot(tt2) - float(np.sum(tt.to_numpy() * tt2.to_numpy()))) < 1e-13
+    assert abs(tt.norm() - float(np.linalg.norm(tt.to_numpy()))) < 1e-13
+    assert abs(dn.dot(cp) - float(np.sum(dn.data * cp.to_numpy()))) < 1e-12
+    assert abs((cp + tt).dot(tt2) - (cp.dot(tt2) + tt.dot(tt2))) < 1e-13
+    flat = rng.choice(int(np.prod(shape)), 40, replace=False)
+    idx = np.stack(np.unravel_index(flat, shape)).astype(np.int64)
+    sp = SparseTensor(shape, idx, rng.standard_normal(40))
+    assert np.allclose(cp.gather(idx), cp.to_numpy()[tuple(idx)])
+    probe = np.stack([rng.integers(0, n, 30) for n in shape])
+    assert np.allclose(sp.gather(probe), sp.to_numpy()[tuple(probe)])
+    assert abs(sp.dot(cp) - float(np.sum(sp.to_numpy() * cp.to_numpy()))) < 1e-13
+    exact = float(np.linalg.norm(cp.to_numpy() - dn.data))
+    assert abs(cp.error(dn) - exact) < 1e-12 and abs(cp.error(dn, fast=True) - exact) < 1e-7 * exact
+    assert abs(cp.error(dn, relative=True) - exact / float(np.linalg.norm(dn.data))) < 1e-12
+
+
+def test_dense_gaussian_drm_matrices_bit_identical_to_reference():
+    """DenseGaussianDRM draws its matrices on the host (legacy MT19937 stream, reference dense_gaussian_drm.py:36-56):
+    bit-identical to the reference's, for the full DRM, a slice and a rank increase; the global NumPy generator is
+    left alone."""
+    from _golden import load, stored_list
+    from tt_sketch.drm import DenseGaussianDRM
+
+    z = load("tucker_dense_gauss.npz")
+    shape = (5, 6, 7, 4)
+    lrank, rrank = tuple(int(x) for x in z["dg_lrank"]), tuple(int(x) for x in z["dg_rrank"])
+    np.random.seed(1234)
+    probe = np.random.uniform()
+    np.random.seed(1234)
+    L = DenseGaussianDRM(lrank, shape=shape, transpose=False, seed=11)
+    R = DenseGaussianDRM(rrank, shape=shape, transpose=True, seed=23)
+    assert np.random.uniform() == probe
+    for drm, key in ((L, "dg_L_mat"), (R, "dg_R_mat"), (L.slice((1, 1, 0), (3, 3, 2)), "dg_Lslice_mat"),
+                     (L.increase_rank((4, 5, 4)), "dg_Linc_mat")):
+        want = stored_list(z, key)
+        assert len(drm.sketching_mats) == len(want)
+        for a, b in zip(drm.sketching_mats, want):
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    assert L.rank == lrank and R.rank == rrank[::-1]
+
+
+def test_tucker_tensor_container_semantics():
+    """TuckerTensor (reference tensor.py:746-816): shape / rank / size, transposition, scaling, dense reconstruction and
+    the seeded random constructor (orthonormal factor rows)."""
+    from tt_sketch.tensor import TuckerTensor
+
+    X = TuckerTensor.random((6, 7, 8), (2, 9, 3), seed=5)
+    assert X.shape == (6, 7, 8) and X.rank == (2, 7, 3) and X.size == 2 * 7 * 3 + 2 * 6 + 7 * 7 + 3 * 8
+    for U in X.factors:
+        assert np.allclose(U @ U.T, np.eye(U.shape[0]), atol=1e-12)
+    dense = np.einsum("abc,ai,bj,ck->ijk", X.core, *X.factors)
+    assert np.allclose(X.to_numpy(), dense, atol=1e-13)
+    assert np.allclose(X.T.to_numpy(), dense.transpose(2, 1, 0), atol=1e-13)
+    assert np.allclose((2.5 * X).to_numpy(), 2.5 * dense, atol=1e-13)
+    Y = TuckerTensor.random((6, 7, 8), (2, 9, 3), seed=5)
+    assert np.array_equal(X.core, Y.core) and all(np.array_equal(a, b) for a, b in zip(X.factors, Y.factors))

@@ -18,8 +18,8 @@ hdr, units, data = rows[0], rows[1], rows[2:]
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "smsp__issue_active.avg.per_cycle_active", "smsp__inst_executed.sum", "smsp__inst_executed_pipe_fp64.sum",
-        "launch__registers_per_thread",
+        "smsp__issue_active.avg.per_cycle_active", "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "smsp__warps_active.avg.per_cycle_active",
         "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
@@ -45,14 +45,20 @@ def scale(v, u):
 
 kn, ti = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
 ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-fi = hdr.index("smsp__inst_executed_pipe_fp64.sum") if "smsp__inst_executed_pipe_fp64.sum" in hdr else None
+# FP64-pipe warp instructions: the --set full sections carry the pipe's utilisation, not the raw count; the pipe
+# issues one warp instruction per two cycles and sub-partition, so count = pct / 100 * 0.5 * (active SM cycles * 4)
+pi = hdr.index("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")
+ci = hdr.index("TPC.TriageCompute.sm__cycles_active.avg") if "TPC.TriageCompute.sm__cycles_active.avg" in hdr else hdr.index("sm__cycles_active.avg")
+gi = hdr.index("launch__grid_size")
+N_SM = 148
 ai = hdr.index("smsp__inst_executed.sum")
 kernels = []
 for r in data:
     kernels.append({"kernel": r[kn], "ms": float(r[ti]) * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(units[ti], 1.0),
                     "dram_bytes": scale(r[ri], units[ri]) + scale(r[wi], units[wi]),
                     "warp_instructions": float(r[ai]),
-                    "fp64_pipe_warp_instructions": float(r[fi]) if fi is not None else None})
+                    "fp64_pipe_pct_of_peak": float(r[pi]),
+                    "fp64_pipe_warp_instructions": float(r[pi]) / 100.0 * 0.5 * float(r[ci]) * 4 * min(N_SM, int(float(r[gi])))})
 tot = sum(k["dram_bytes"] for k in kernels)
 fp64 = sum(k["fp64_pipe_warp_instructions"] or 0.0 for k in kernels)
 json.dump({"nnz": nnz, "source": f"ncu --set full, profiles/{os.path.basename(out)}", "kernels": kernels,

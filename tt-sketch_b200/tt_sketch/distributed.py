@@ -255,13 +255,13 @@ class _GpuSequentialOps:
 
     def __init__(self, part: Optional[Tensor], left_drm, right_drm, shape):
         from tt_sketch import _backend as be
-        from tt_sketch.sketch_dispatch import (OMEGA_DEVICE, PSI_DEVICE, OrthogTTDRM, _check_supported, _summands,
+        from tt_sketch.sketch_dispatch import (OrthogTTDRM, _check_supported, _summands, device_operators,
                                                get_sketch_method)
 
         self.be, self.shape, self.d = be, tuple(shape), len(shape)
         self.parts = _summands(part) if part is not None else []
         self.rL, self.rR = tuple(left_drm.bond_rank), tuple(right_drm.bond_rank)
-        self.om, self.ps = OMEGA_DEVICE, PSI_DEVICE
+        self.ops = device_operators
         for X in self.parts:
             _check_supported(X, left_drm)
             _check_supported(X, right_drm)
@@ -274,7 +274,7 @@ class _GpuSequentialOps:
         for mu in range(self.d - 1):
             o = self.be.zeros((self.rL[mu], self.rR[mu]))
             for s, X in enumerate(self.parts):
-                self.om[type(X)](self.Lc[s][mu], self.Rc[s][mu], tensor=X, mu=mu, out=o)
+                self.ops(type(X))[0](self.Lc[s][mu], self.Rc[s][mu], tensor=X, mu=mu, out=o)
             out.append(o)
         self.Lc = None
         return out
@@ -288,7 +288,7 @@ class _GpuSequentialOps:
             self.left_psi.add_core(prev_core)
             lefts = next(self.left_psi)
         for s, X in enumerate(self.parts):
-            self.ps[type(X)](lefts[s], self.Rc[s][mu] if mu < self.d - 1 else None, tensor=X, mu=mu, out=P)
+            self.ops(type(X))[1](lefts[s], self.Rc[s][mu] if mu < self.d - 1 else None, tensor=X, mu=mu, out=P)
         return P
 
     def orth(self, P, Omega):

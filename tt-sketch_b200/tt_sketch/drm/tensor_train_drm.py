@@ -5,7 +5,7 @@ values (cores come from TensorTrain.random(..., norm_goal="norm-preserve") on th
 the reference's generator depends on the host's cpu_count(); they are uploaded once), same
 `sketch_sparse / sketch_tt / sketch_cp / sketch_dense` generators.  Every contraction is a
 libttsk kernel: strided FP64 GEMMs for TT / CP / dense input, the per-nonzero chain kernel for
-sparse input.  `sketch_tucker` is out of scope.
+sparse input, `sketch_tucker` (:124-145) included.
 """
 from __future__ import annotations
 
@@ -16,11 +16,11 @@ import numpy as np
 from tt_sketch import _backend as be
 from tt_sketch.drm_base import CanSlice, handle_transpose
 from tt_sketch.sketching_methods.abstract_methods import (CansketchCP, CansketchDense, CansketchSparse,
-                                                          CansketchTT)
-from tt_sketch.tensor import CPTensor, DenseTensor, SparseTensor, TensorTrain
+                                                          CanSketchTucker, CansketchTT)
+from tt_sketch.tensor import CPTensor, DenseTensor, SparseTensor, TensorTrain, TuckerTensor
 
 
-class TensorTrainDRM(CansketchSparse, CansketchTT, CansketchCP, CanSlice, CansketchDense):
+class TensorTrainDRM(CansketchSparse, CansketchTT, CansketchCP, CanSlice, CansketchDense, CanSketchTucker):
     kind = be.DRM_TT
 
     def __init__(self, rank: Union[Tuple[int, ...], int], shape: Tuple[int, ...], transpose: bool,
@@ -127,4 +127,27 @@ class TensorTrainDRM(CansketchSparse, CansketchTT, CansketchCP, CanSlice, Canske
             r0, n, r1 = g.shape
             pc = be.gemm(pc, g.reshape(r0, n * r1)).reshape(-1, r1)
             yield pc.T
+            mu += 1
+
+    # ------------------------------------------------------------------ Tucker
+    @handle_transpose
+    def sketch_tucker_device(self, tensor: TuckerTensor):
+        """pc_mu (prod(s_0..s_mu), r_D): the DRM cores contracted with the Tucker factors mode by mode.  Like the
+        reference (tensor_train_drm.py:124-145) this takes the whole DRM: a rank slice is refused."""
+        if tuple(self.rank) != tuple(self.true_rank):
+            raise ValueError("a sliced TensorTrainDRM cannot sketch a TuckerTensor (the reference reshapes to the "
+                             "unsliced rank)")
+        factors = tensor.device()["factors"]
+        pc, mu = None, 0
+        while mu < len(self.cores):
+            g, U = self.device_core(mu), factors[mu]      # (r0, n, r1), (s, n)
+            r0, n, r1 = g.shape
+            s = U.shape[0]
+            if mu == 0:
+                pc = be.gemm(U, g.reshape(n, r1))
+            else:
+                red = be.empty((r0, s, r1))               # red[j] = U @ g[j]
+                be.gemm_batched(U.unsqueeze(0).expand(r0, s, n), g, red)
+                pc = be.gemm(pc, red.reshape(r0, s * r1)).reshape(-1, r1)
+            yield pc
             mu += 1

@@ -26,7 +26,7 @@ from tt_sketch.drm import SparseGaussianDRM, TensorTrainDRM
 from tt_sketch.drm_base import DRM
 from tt_sketch.sketch_container import SketchContainer
 from tt_sketch.sketching_methods.abstract_methods import (CansketchCP, CansketchDense, CansketchSparse,
-                                                          CansketchTT)
+                                                          CanSketchTucker, CansketchTT)
 from tt_sketch.sketching_methods.cp_sketch import (omega_cp_device, psi_cp_device, sketch_omega_cp,
                                                    sketch_psi_cp)
 from tt_sketch.sketching_methods.dense_sketch import (omega_dense_device, psi_dense_device,
@@ -35,7 +35,9 @@ from tt_sketch.sketching_methods.sparse_sketch import (omega_sparse_device, psi_
                                                        sketch_omega_sparse, sketch_psi_sparse)
 from tt_sketch.sketching_methods.tensor_train_sketch import (omega_tt_device, psi_tt_device,
                                                              sketch_omega_tt, sketch_psi_tt)
-from tt_sketch.tensor import CPTensor, DenseTensor, SparseTensor, Tensor, TensorSum, TensorTrain
+from tt_sketch.sketching_methods.tucker_sketch import (omega_tucker_device, psi_tucker_device,
+                                                       sketch_omega_tucker, sketch_psi_tucker)
+from tt_sketch.tensor import CPTensor, DenseTensor, SparseTensor, Tensor, TensorSum, TensorTrain, TuckerTensor
 from tt_sketch.utils import right_mul_pinv  # noqa: F401  (re-exported like the reference)
 
 ABSTRACT_TENSOR_SKETCH_DISPATCH = {
@@ -43,6 +45,7 @@ ABSTRACT_TENSOR_SKETCH_DISPATCH = {
     TensorTrain: CansketchTT,
     DenseTensor: CansketchDense,
     CPTensor: CansketchCP,
+    TuckerTensor: CanSketchTucker,
 }
 
 # tensor class -> name of the DRM method that contracts the DRM with it (host arrays)
@@ -51,6 +54,7 @@ DRM_SKETCH_METHOD_DISPATCH = {
     TensorTrain: "sketch_tt",
     DenseTensor: "sketch_dense",
     CPTensor: "sketch_cp",
+    TuckerTensor: "sketch_tucker",
 }
 
 # the plug-in point: NumPy-in / NumPy-out operators, mutable like the reference's dicts
@@ -59,12 +63,14 @@ OMEGA_METHODS = {
     TensorTrain: sketch_omega_tt,
     DenseTensor: sketch_omega_dense,
     CPTensor: sketch_omega_cp,
+    TuckerTensor: sketch_omega_tucker,
 }
 PSI_METHODS = {
     SparseTensor: sketch_psi_sparse,
     TensorTrain: sketch_psi_tt,
     DenseTensor: sketch_psi_dense,
     CPTensor: sketch_psi_cp,
+    TuckerTensor: sketch_psi_tucker,
 }
 
 # device-resident twins used by general_sketch (accumulate into `out`)
@@ -73,12 +79,14 @@ OMEGA_DEVICE = {
     TensorTrain: omega_tt_device,
     DenseTensor: omega_dense_device,
     CPTensor: omega_cp_device,
+    TuckerTensor: omega_tucker_device,
 }
 PSI_DEVICE = {
     SparseTensor: psi_sparse_device,
     TensorTrain: psi_tt_device,
     DenseTensor: psi_dense_device,
     CPTensor: psi_cp_device,
+    TuckerTensor: psi_tucker_device,
 }
 
 
@@ -104,6 +112,42 @@ OMEGA_METHODS[TensorSum] = sketch_omega_sum
 PSI_METHODS[TensorSum] = sketch_psi_sum
 
 
+# The public dicts are the reference's plug-in point: replacing (or adding) an entry must change what the sketching
+# loops run.  `general_sketch` takes the device twin of a tensor type only while its public entries are still the
+# stock ones; otherwise the registered NumPy-in / NumPy-out operator is called on host copies of the DRM
+# contractions and its result is added to the device buffer (and the fused single-call paths are skipped).
+_STOCK_OMEGA, _STOCK_PSI, _STOCK_DRM_METHOD = dict(OMEGA_METHODS), dict(PSI_METHODS), dict(DRM_SKETCH_METHOD_DISPATCH)
+
+
+def _is_stock(t) -> bool:
+    return (t in _STOCK_OMEGA and OMEGA_METHODS.get(t) is _STOCK_OMEGA[t] and PSI_METHODS.get(t) is _STOCK_PSI[t]
+            and DRM_SKETCH_METHOD_DISPATCH.get(t) == _STOCK_DRM_METHOD[t] and t in OMEGA_DEVICE)
+
+
+def _host(x):
+    return None if x is None else np.ascontiguousarray(be.to_host(x))
+
+
+def device_operators(t):
+    """(omega, psi) with the device-twin signature `(L, R, *, tensor, mu, out)` for tensor class `t`."""
+    if _is_stock(t):
+        return OMEGA_DEVICE[t], PSI_DEVICE[t]
+    if t not in OMEGA_METHODS or t not in PSI_METHODS:
+        raise ValueError(f"no Omega / Psi method registered for {t}")
+
+    def omega(L, R, *, tensor, mu, out, **kw):
+        res = OMEGA_METHODS[t](_host(L), _host(R), tensor=tensor, mu=mu, omega_shape=tuple(out.shape))
+        out += be.to_device(np.asarray(res, dtype=np.float64).reshape(tuple(out.shape)))
+        return out
+
+    def psi(L, R, *, tensor, mu, out, **kw):
+        res = PSI_METHODS[t](_host(L), _host(R), tensor=tensor, mu=mu, psi_shape=tuple(out.shape))
+        out += be.to_device(np.asarray(res, dtype=np.float64).reshape(tuple(out.shape)))
+        return out
+
+    return omega, psi
+
+
 def sum_sketch(tensor: TensorSum, *, drm: DRM):
     """Per-summand DRM contractions advanced in lock step: yields one tuple per bond."""
     gens = [get_sketch_method(X, drm)(X) for X in tensor.tensors]
@@ -114,6 +158,9 @@ def sum_sketch(tensor: TensorSum, *, drm: DRM):
 def get_sketch_method(tensor: Tensor, drm: DRM, device: bool = False) -> Callable:
     name = DRM_SKETCH_METHOD_DISPATCH.get(type(tensor))
     if name is not None:
+        if device and not hasattr(drm, name + "_device"):  # a plugged-in host-only contraction: upload what it yields
+            host_method = getattr(drm, name)
+            return lambda X: (be.to_device(np.ascontiguousarray(m), np.float64) for m in host_method(X))
         return getattr(drm, name + "_device" if device else name)
     if isinstance(tensor, TensorSum):
         return partial(sum_sketch, drm=drm)
@@ -179,8 +226,9 @@ def _summands(tensor: Tensor) -> List[Tensor]:
 def _check_supported(X: Tensor, drm: DRM):
     if type(X) not in DRM_SKETCH_METHOD_DISPATCH:
         raise ValueError(f"DRM of type {type(drm)} can't sketch {type(X)}")
-    name = DRM_SKETCH_METHOD_DISPATCH[type(X)] + "_device"
-    getattr(drm, name)  # AttributeError if the DRM lacks the capability (like the reference)
+    name = DRM_SKETCH_METHOD_DISPATCH[type(X)]
+    if not hasattr(drm, name + "_device"):
+        getattr(drm, name)  # AttributeError if the DRM lacks the capability (like the reference)
 
 
 def drm_descriptor(drm: DRM):
@@ -274,22 +322,23 @@ def streaming_sketch_device(tensor: Tensor, left_drm: DRM, right_drm: DRM, packe
     for X in _summands(tensor):
         if tuple(X.shape) != shape:
             raise ValueError(f"Shape {left_drm.shape} of DRM doesn't match tensor's shape {X.shape}")
-        if _fusable(X, left_drm, right_drm):
+        stock = _is_stock(type(X))
+        if stock and _fusable(X, left_drm, right_drm):
             if tuple(left_drm.shape) != shape or tuple(right_drm.shape) != shape:
                 raise ValueError(f"Shape {left_drm.shape} of DRM doesn't match tensor's shape {shape}")
             _fused_sparse(X, left_drm, right_drm, packed, accumulate=True)
             continue
-        if _fusable_tt(X, left_drm, right_drm):
+        if stock and _fusable_tt(X, left_drm, right_drm):
             _fused_tt(X, left_drm, right_drm, packed)
             continue
-        if _fusable_dense(X, left_drm, right_drm):
+        if stock and _fusable_dense(X, left_drm, right_drm):
             _fused_dense(X, left_drm, right_drm, packed)
             continue
         _check_supported(X, left_drm)
         _check_supported(X, right_drm)
         Lc = list(get_sketch_method(X, left_drm, device=True)(X))
         Rc = list(get_sketch_method(X, right_drm, device=True)(X))
-        om, ps = OMEGA_DEVICE[type(X)], PSI_DEVICE[type(X)]
+        om, ps = device_operators(type(X))
         for mu in range(d - 1):
             om(Lc[mu], Rc[mu], tensor=X, mu=mu, out=views[d + mu])
         for mu in range(d):
@@ -316,7 +365,7 @@ def _sequential_sketch(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, 
         for mu in range(d - 1):
             o = be.zeros((rL[mu], rR[mu]))
             for s, X in enumerate(parts):
-                OMEGA_DEVICE[type(X)](Lc[s][mu], Rc[s][mu], tensor=X, mu=mu, out=o)
+                device_operators(type(X))[0](Lc[s][mu], Rc[s][mu], tensor=X, mu=mu, out=o)
             Omega.append(o)
         del Lc
     else:
@@ -332,7 +381,7 @@ def _sequential_sketch(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, 
             lefts = next(left_psi)
         P = be.zeros((r1, shape[mu], r2))
         for s, X in enumerate(parts):
-            PSI_DEVICE[type(X)](lefts[s], Rc[s][mu] if mu < d - 1 else None, tensor=X, mu=mu, out=P)
+            device_operators(type(X))[1](lefts[s], Rc[s][mu] if mu < d - 1 else None, tensor=X, mu=mu, out=P)
         if mu < d - 1:
             P = orth_step_device(P, Omega[mu] if method == SketchMethod.orthogonal else None)
         Psi.append(P)

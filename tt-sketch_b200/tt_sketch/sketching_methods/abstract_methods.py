@@ -59,3 +59,15 @@ class CansketchCP(DRM, ABC):
 
     def sketch_cp(self, tensor) -> ArrayGenerator:
         return _DeviceTwin.host(self.sketch_cp_device(tensor))
+
+
+class CanSketchTucker(DRM, ABC):
+    """sketch_tucker -> (prod(tensor.rank[:mu+1]), rank[mu]): the DRM contracted with the first mu+1 Tucker
+    factors (reference abstract_methods.py:54-63)."""
+
+    @abstractmethod
+    def sketch_tucker_device(self, tensor):
+        ...
+
+    def sketch_tucker(self, tensor) -> ArrayGenerator:
+        return _DeviceTwin.host(self.sketch_tucker_device(tensor))

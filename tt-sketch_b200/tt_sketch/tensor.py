@@ -2,9 +2,9 @@
 
 Same class names, constructors and attributes as tt_sketch/tensor.py of the reference for
 DenseTensor (:140), SparseTensor (:186), TensorTrain (:294), TensorSum (:612) and CPTensor
-(:674).  Only what the sketching hot path and its tests need is provided; the tensor
-algebra that is not sketching (round, dot, gather, svdvals, orthogonalize, TuckerTensor) is
-out of scope.  Containers additionally cache device copies of their
+(:674) and TuckerTensor (:746).  What the sketching hot path, its tests and the validation step after it
+need is provided (dot / norm / error / gather; TensorTrain.gather runs on the device); round, svdvals and
+orthogonalize are out of scope.  Containers additionally cache device copies of their
 arrays (`.device()`), keyed by CUDA device and by the identity of the host arrays.
 """
 from __future__ import annotations
@@ -59,18 +59,37 @@ class Tensor(ABC):
     def __sub__(self, other):
         return self + (-other)
 
+    def dot(self, other, reverse: bool = False) -> float:
+        """Inner product (reference tensor.py:121-129): a TensorSum distributes, the other operand is asked first
+        (a SparseTensor only needs `other.gather`), dense reconstruction is the last resort."""
+        if isinstance(other, TensorSum):
+            return other.dot(self)
+        if not reverse:
+            return other.dot(self, reverse=True)
+        return float(np.dot(self.to_numpy().reshape(-1), other.to_numpy().reshape(-1)))
+
     def norm(self) -> float:
-        return float(np.linalg.norm(self.to_numpy()))
+        return float(np.sqrt(np.abs(self.dot(self))))
 
     def error(self, other, relative: bool = False, rmse: bool = False, fast: bool = False) -> float:
-        """Frobenius distance to `other` through dense reconstruction (small tensors only)."""
-        b = other if isinstance(other, np.ndarray) else other.to_numpy()
-        err = float(np.linalg.norm(self.to_numpy() - b))
+        """Frobenius distance to `other` (reference tensor.py:52-87): through dense reconstruction, or with
+        `fast=True` through the inner-product formula (norms and one dot product; for a SparseTensor against a
+        TensorTrain that is one device gather at the nonzeros -- how errors are sampled on tensors too large to
+        densify; inaccurate below relative errors of about 1e-8, like the reference says)."""
+        if isinstance(other, np.ndarray):
+            other = DenseTensor(other)
+        other_norm = other.norm()
+        if fast:
+            self_norm = self.norm()
+            dot = self.dot(other)
+            norm_sum = self_norm ** 2 + other_norm ** 2
+            err = float(np.sqrt(norm_sum) * np.sqrt(np.abs(1 - 2 * dot / norm_sum)))
+        else:
+            err = float(np.linalg.norm(self.to_numpy() - other.to_numpy()))
         if relative:
-            nb = float(np.linalg.norm(b))
-            if nb == 0:
+            if other_norm == 0:
                 return float("inf")
-            err /= nb
+            err /= other_norm
         if rmse:
             err /= float(np.sqrt(np.prod(self.shape)))
         return err
@@ -125,6 +144,9 @@ class DenseTensor(Tensor):
 
     def to_numpy(self):
         return self.data
+
+    def norm(self) -> float:
+        return float(np.linalg.norm(self.data))
 
     def to_sparse(self) -> "SparseTensor":
         idx = np.indices(self.shape).reshape(self.ndim, -1)
@@ -191,6 +213,25 @@ class SparseTensor(Tensor):
 
     def norm(self) -> float:
         return float(np.linalg.norm(self.entries))
+
+    def dot(self, other, reverse: bool = False) -> float:
+        """sum_p entries[p] * other[indices[:, p]] when `other` can gather (reference tensor.py:250-255)."""
+        if hasattr(other, "gather"):
+            return float(np.dot(other.gather(self.indices), self.entries))
+        return super().dot(other, reverse=reverse)
+
+    def gather(self, indices) -> npt.NDArray[np.float64]:
+        """Entries at the given multi-indices, 0 where nothing is stored (reference tensor.py:275-291; duplicates of
+        a stored index: the last one wins, like the reference's dict)."""
+        flat = np.ravel_multi_index(tuple(np.asarray(r) for r in indices), self.shape)
+        own = np.ravel_multi_index(tuple(np.asarray(r) for r in self.indices), self.shape)
+        order = np.argsort(own, kind="stable")
+        own_sorted = own[order]
+        pos = np.searchsorted(own_sorted, flat, side="right") - 1
+        hit = (pos >= 0) & (own_sorted[np.clip(pos, 0, None)] == flat)
+        out = np.zeros(len(flat))
+        out[hit] = np.asarray(self.entries)[order[pos[hit]]]
+        return out
 
     def __mul__(self, other: float) -> "SparseTensor":
         return SparseTensor(self.shape, self.indices, self.entries * other)
@@ -294,6 +335,35 @@ class TensorTrain(Tensor):
     def __setitem__(self, i: int, data) -> None:
         self.cores[i] = data
 
+    def gather(self, idx) -> npt.NDArray[np.float64]:
+        """One entry of the represented tensor per column of `idx` (d x N): the chained products of the core slices
+        at the indices, left to right (reference tensor.py:414-440, which loops over every slice of every mode).
+        Runs on the GPU with the per-nonzero chain kernel of the TT-DRM (`ttsk_ttdrm_sparse_step`): this is how errors
+        are sampled on sparse tensors too large to densify."""
+        from tt_sketch import _backend as be
+
+        idx = np.ascontiguousarray(np.stack([np.asarray(r) for r in idx]) if not isinstance(idx, np.ndarray) else idx,
+                                   dtype=np.int64)
+        if idx.shape[0] != self.ndim:
+            raise ValueError(f"gather needs {self.ndim} index rows, got {idx.shape[0]}")
+        if idx.shape[1] == 0:
+            return np.zeros(0)
+        d_idx = be.to_device(idx, np.int64)
+        cores = self.device()["cores"]
+        v = None
+        for mu in range(self.ndim):
+            v = be.ttdrm_sparse_step(d_idx[mu], v, cores[mu])
+        return be.to_host(v).reshape(-1)
+
+    def dot(self, other, reverse: bool = False) -> float:
+        """TT . TT in a left-to-right sweep (reference tensor.py:542-560); anything else through the base class."""
+        if isinstance(other, TensorTrain):
+            res = np.einsum("ijk,ljm->km", self.cores[0], other.cores[0])
+            for c1, c2 in zip(self.cores[1:], other.cores[1:]):
+                res = np.einsum("ij,ika,jkb->ab", res, c1, c2, optimize="optimal")
+            return float(np.sum(res))
+        return super().dot(other, reverse=reverse)
+
     def __mul__(self, other: float) -> "TensorTrain":
         cores = [c.copy() for c in self.cores]
         cores[-1] = cores[-1] * other
@@ -349,6 +419,13 @@ class CPTensor(Tensor):
     def __setitem__(self, i: int, data) -> None:
         self.cores[i] = data
 
+    def gather(self, idx) -> npt.NDArray[np.float64]:
+        """Values at the given indices (reference tensor.py:726-732)."""
+        res = 1
+        for C, i in zip(self.cores, idx):
+            res = res * np.asarray(C)[np.asarray(i)]
+        return np.sum(res, axis=1)
+
     def __mul__(self, other: float) -> "CPTensor":
         cores = list(self.cores)
         cores[0] = cores[0] * other
@@ -369,6 +446,62 @@ class CPTensor(Tensor):
                 all(c is pc for c, pc in zip(self.cores, reversed(parent.cores))):
             return {"cores": list(reversed(pd["cores"]))}
         return {"cores": [be.to_device(c, np.float64) for c in self.cores]}
+
+
+class TuckerTensor(Tensor):
+    """Tucker format (reference tensor.py:746-816): a core of shape `rank` = (s_1..s_d) and d factor matrices
+    `factors[i]` of shape (s_i, n_i)."""
+
+    def __init__(self, factors: ArrayList, core: npt.NDArray) -> None:
+        self.core = core
+        self.factors = factors
+        self.shape = tuple(U.shape[1] for U in factors)
+        self.rank = tuple(U.shape[0] for U in factors)
+
+    @property
+    def T(self) -> "TuckerTensor":
+        return TuckerTensor(self.factors[::-1], np.transpose(self.core))
+
+    @property
+    def size(self) -> int:
+        return int(self.core.size + sum(U.size for U in self.factors))
+
+    def to_numpy(self):
+        out = self.core
+        for i, U in enumerate(self.factors):  # mode-i product with U_i^T, one mode at a time
+            out = np.moveaxis(np.tensordot(out, U, axes=([i], [0])), -1, i)
+        return out
+
+    def __mul__(self, other: float) -> "TuckerTensor":
+        return TuckerTensor(self.factors, self.core * other)
+
+    def __repr__(self) -> str:
+        return f"<Tucker tensor of shape {self.shape} and rank {self.rank} at {hex(id(self))}>"
+
+    @classmethod
+    def random(cls, shape, rank, seed: Optional[int] = None) -> "TuckerTensor":
+        """Gaussian core, orthonormal-row factors; same draws as the reference (tensor.py:792-816: the core seed is
+        the first word of the SeedSequence state, the factor seeds its first d words)."""
+        d = len(shape)
+        try:
+            ranks = tuple(rank)
+        except TypeError:
+            ranks = (rank,) * d
+        ranks = tuple(min(int(r), int(n)) for r, n in zip(ranks, shape))
+        seq = SeedSequence(seed)
+        core = random_normal(shape=ranks, seed=seq.generate_state(1)[0])
+        factors = [np.linalg.qr(random_normal(shape=(r, n), seed=s).T)[0].T
+                   for r, n, s in zip(ranks, shape, seq.generate_state(d))]
+        return cls(factors, core)
+
+    def _host_arrays_id(self):
+        return (id(self.core),) + tuple(id(U) for U in self.factors)
+
+    def _upload(self):
+        from tt_sketch import _backend as be
+
+        return {"core": be.to_device(self.core, np.float64),
+                "factors": [be.to_device(U, np.float64) for U in self.factors]}
 
 
 class TensorSum(Tensor):
@@ -395,6 +528,9 @@ class TensorSum(Tensor):
         for X in self.tensors:
             out += X.to_numpy()
         return out
+
+    def dot(self, other, reverse: bool = False) -> float:
+        return float(sum(X.dot(other, reverse) for X in self.tensors))
 
     def __iadd__(self, other) -> "TensorSum":
         self.tensors.extend(other.tensors if isinstance(other, TensorSum) else [other])
