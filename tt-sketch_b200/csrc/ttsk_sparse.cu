@@ -228,12 +228,20 @@ __global__ void __launch_bounds__(kPartBins) part_l1base_kernel(const int* __res
 //          digit = key >> 7, destination = the CTA's own cursor of the coarse bucket (shared memory, no atomics).
 // LEVEL 2: elements are the words of the first sweep, walked per coarse bucket (tile map `tstart`), digit = key & 127,
 //          destination cursor cursor[key].
-template <int LEVEL>
+//
+// PAY (payload partition, for passes that only gather table rows): the element is a PAIR of words -- w = key << kshift |
+// row of table A << bshift | row of table B, and the nonzero's value -- formed in the first sweep from the packed
+// records (read in input order, i.e. coalesced) instead of (key << 32 | id): the pass then streams everything it
+// needs per nonzero in sorted order and never touches the records (one random 32-byte read per nonzero, a 128-byte
+// DRAM access, in the id form).
+
+template <int LEVEL, bool PAY>
 __global__ void __launch_bounds__(kPartThreads) partition_kernel(const long long* __restrict__ keys,
                                                                 const unsigned long long* __restrict__ in_words, long long n,
                                                                 int n_mu, const int* __restrict__ offs,
                                                                 const int* __restrict__ tstart, int* __restrict__ cursors,
-                                                                unsigned long long* __restrict__ out_words, long long block_len) {
+                                                                unsigned long long* __restrict__ out_words, long long block_len,
+                                                                int kshift, const PayPlan pp) {
     // every warp ranks its elements in its OWN row of counters (one address hit by all 16 warps serialises at the
     // bank: the first sweep has only ~80 live digits); a prefix over the warps then places the rows of a digit
     __shared__ int s_wcnt[kPartThreads / 32][kPartBins];
@@ -271,14 +279,33 @@ __global__ void __launch_bounds__(kPartThreads) partition_kernel(const long long
         }
         __syncthreads();
         const long long lo = s_range[0], hi = s_range[1];
-        unsigned long long w[kPartPer];
+        unsigned long long w[kPartPer], pay[PAY ? kPartPer : 1];
         int rank[kPartPer];
 #pragma unroll
         for (int u = 0; u < kPartPer; u++) {
             const long long p = lo + tid + (long long)u * kPartThreads;
             if (p < hi) {
-                if (LEVEL == 1) w[u] = ((unsigned long long)(unsigned)__ldcs(keys + p) << 32) | (unsigned long long)(unsigned)p;
-                else w[u] = __ldcs(in_words + p);
+                if (LEVEL == 1 && PAY) {
+                    const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(pp.recs + p * 8));
+                    const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(pp.recs + p * 8) + 1);
+                    const unsigned wd[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    unsigned long long a = 0, b = 0;
+#pragma unroll
+                    for (int m = 0; m < 6; m++) {
+                        a += (unsigned long long)wd[2 + m] * pp.smul_a[m];
+                        b += (unsigned long long)wd[2 + m] * pp.smul_b[m];
+                    }
+                    unsigned key = 0;
+#pragma unroll
+                    for (int m = 2; m < 8; m++) key = (m == pp.key_word) ? wd[m] : key;
+                    w[u] = ((unsigned long long)key << kshift) | (a << pp.bshift) | b;
+                    pay[u] = ((unsigned long long)r0.y << 32) | r0.x;
+                } else if (LEVEL == 1) {
+                    w[u] = ((unsigned long long)(unsigned)__ldcs(keys + p) << 32) | (unsigned long long)(unsigned)p;
+                } else {
+                    w[u] = __ldcs(in_words + p);
+                    if (PAY) pay[u] = __ldcs(pp.in_pay + p);
+                }
             } else {
                 w[u] = ~0ull;
             }
@@ -286,7 +313,7 @@ __global__ void __launch_bounds__(kPartThreads) partition_kernel(const long long
 #pragma unroll
         for (int u = 0; u < kPartPer; u++) {
             if (w[u] != ~0ull) {
-                const int key = (int)(w[u] >> 32);
+                const int key = (int)(w[u] >> kshift);
                 const int dgt = (LEVEL == 1) ? (key >> 7) : (key & (kPartBins - 1));
                 rank[u] = atomicAdd(&s_wcnt[warp][dgt], 1);
             }
@@ -326,23 +353,45 @@ __global__ void __launch_bounds__(kPartThreads) partition_kernel(const long long
         __syncthreads();
         // the tile in digit order in shared memory, then out in runs: consecutive threads write consecutive words of
         // a run (a lane-per-element scatter costs one L2 sector write per word, the limit of these sweeps)
+        int pos[PAY ? kPartPer : 1];
 #pragma unroll
         for (int u = 0; u < kPartPer; u++) {
             if (w[u] != ~0ull) {
-                const int key = (int)(w[u] >> 32);
+                const int key = (int)(w[u] >> kshift);
                 const int dgt = (LEVEL == 1) ? (key >> 7) : (key & (kPartBins - 1));
-                s_out[s_loc[dgt] + s_wcnt[warp][dgt] + rank[u]] = w[u];
+                const int at = s_loc[dgt] + s_wcnt[warp][dgt] + rank[u];
+                s_out[at] = w[u];
+                if (PAY) pos[u] = at;
             }
         }
         __syncthreads();
         const int n_here = (int)(hi - lo);
-        for (int i = tid; i < n_here; i += kPartThreads) {
-            const unsigned long long x = s_out[i];
-            const int key = (int)(x >> 32);
-            const int dgt = (LEVEL == 1) ? (key >> 7) : (key & (kPartBins - 1));
-            out_words[s_base[dgt] + (i - s_loc[dgt])] = x;
+        int dst[PAY ? kPartPer : 1];
+#pragma unroll
+        for (int u = 0; u < kPartPer; u++) {
+            const int i = tid + u * kPartThreads;
+            if (i < n_here) {
+                const unsigned long long x = s_out[i];
+                const int key = (int)(x >> kshift);
+                const int dgt = (LEVEL == 1) ? (key >> 7) : (key & (kPartBins - 1));
+                const int at = s_base[dgt] + (i - s_loc[dgt]);
+                out_words[at] = x;
+                if (PAY) dst[u] = at;
+            }
         }
         __syncthreads();
+        if (PAY) {  // the values take the same route through the tile buffer
+#pragma unroll
+            for (int u = 0; u < kPartPer; u++)
+                if (w[u] != ~0ull) s_out[pos[u]] = pay[u];
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < kPartPer; u++) {
+                const int i = tid + u * kPartThreads;
+                if (i < n_here) pp.out_pay[dst[u]] = s_out[i];
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -529,6 +578,8 @@ struct SortBufs {
     int* hist; int* offs; int* cursor;
     int* cta_cnt;  // per-CTA key counts / range starts of the two-level scatter
     unsigned long long* part_tmp;  // words after the first sweep of the two-level partition
+    unsigned long long* pay_tmp;   // payload partition: values after the first sweep
+    unsigned long long* payv;      // payload partition: values in sorted order (next to keyid)
     int* part_aux;                 // tile map of the second sweep [129], then the (CTA, coarse bucket) starts of the first [CTAs][128]
     // TT DRMs bucket a mode up to three times (chain level of either side + the mode pass): with n_modes > 0 every
     // mode keeps its own sorted words / segment starts for the chunk and is bucketed once
@@ -544,7 +595,7 @@ static int rec_words_for(int d) { return d <= 0 ? 0 : (int)align_up(2 + d, 8); }
 constexpr int kMaxSortCtas = 2 * 160;  // the two-level scatter runs two CTAs per SM
 static int64_t cta_cnt_bytes(int64_t n_max) { return n_max <= kLocalBins ? (int64_t)kMaxSortCtas * n_max * 4 : 256; }
 static int64_t sortbufs_bytes(int64_t n_max, int64_t chunk, int d, int per_mode = 0) {
-    return 3 * align_up((n_max + 1) * 4, 256) + 2 * align_up(chunk * 8, 256) + align_up(chunk * 4 * rec_words_for(d), 256) +
+    return 3 * align_up((n_max + 1) * 4, 256) + 4 * align_up(chunk * 8, 256) + align_up(chunk * 4 * rec_words_for(d), 256) +
            align_up(cta_cnt_bytes(n_max), 256) + 4096 + align_up((128 + 8 + (int64_t)kMaxSortCtas * 128) * 4, 256) +
            (per_mode ? (int64_t)d * (align_up(chunk * 8, 256) + align_up((n_max + 1) * 4, 256)) : 0);
 }
@@ -571,8 +622,10 @@ static int carve_sortbufs(ttsk_ctx* ctx, SortBufs& sb, int64_t n_max, int64_t ch
     sb.keyid = (unsigned long long*)ctx->ws_alloc(chunk * 8);
     sb.cta_cnt = (int*)ctx->ws_alloc(cta_cnt_bytes(n_max));
     sb.part_tmp = (unsigned long long*)ctx->ws_alloc(chunk * 8);
+    sb.pay_tmp = (unsigned long long*)ctx->ws_alloc(chunk * 8);
+    sb.payv = (unsigned long long*)ctx->ws_alloc(chunk * 8);
     sb.part_aux = (int*)ctx->ws_alloc((kPartBins + 8 + (int64_t)kMaxSortCtas * kPartBins) * 4);
-    if (!sb.hist || !sb.offs || !sb.cursor || !sb.keyid || !sb.cta_cnt || !sb.part_tmp || !sb.part_aux) {
+    if (!sb.hist || !sb.offs || !sb.cursor || !sb.keyid || !sb.cta_cnt || !sb.part_tmp || !sb.part_aux || !sb.pay_tmp || !sb.payv) {
         set_error("workspace carve failed (sort buffers)");
         return TTSK_E_NOMEM;
     }
@@ -580,8 +633,12 @@ static int carve_sortbufs(ttsk_ctx* ctx, SortBufs& sb, int64_t n_max, int64_t ch
 }
 
 // bucket the chunk by the index row `key_idx`: sb.keyid receives (key << 32 | id) in sorted order
+// With `pay` (see PayPlan) and the two-level partition available, the sorted elements are (word, value) pairs in
+// sb.keyid / sb.payv and *pay_done is set; otherwise the id form is produced as usual.
 static int sort_keys(ttsk_ctx* ctx, int64_t nnz, const long long* key_idx, int64_t n_mu, SortBufs& sb,
-                     cudaStream_t st, int mode = -1) {
+                     cudaStream_t st, int mode = -1, const PayPlan* pay = nullptr, int pay_kshift = 32,
+                     bool* pay_done = nullptr) {
+    if (pay_done) *pay_done = false;
     if (mode >= 0 && mode < sb.n_modes) {
         sb.keyid = sb.keyid_m[mode];
         sb.offs = sb.offs_m[mode];
@@ -621,11 +678,30 @@ static int sort_keys(ttsk_ctx* ctx, int64_t nnz, const long long* key_idx, int64
         TTSK_LAUNCHED(ctx);
         part_setup_kernel<<<1, kPartBins, 0, st>>>(sb.offs, (int)n_mu, tstart);
         TTSK_LAUNCHED(ctx);
-        partition_kernel<1><<<(unsigned)local_grid, kPartThreads, 0, st>>>(key_idx, nullptr, nnz, (int)n_mu, sb.offs, tstart, l1base,
-                                                                          sb.part_tmp, block_len);
+        const unsigned grid2 = (unsigned)std::min<long long>((nnz + kPartTile - 1) / kPartTile, 4LL * ctx->sm_count);
+        if (pay && sb.pay_tmp && sb.payv) {
+            PayPlan pp = *pay;
+            pp.in_pay = nullptr;
+            pp.out_pay = sb.pay_tmp;
+            partition_kernel<1, true><<<(unsigned)local_grid, kPartThreads, 0, st>>>(key_idx, nullptr, nnz, (int)n_mu, sb.offs, tstart,
+                                                                                    l1base, sb.part_tmp, block_len, pay_kshift, pp);
+            TTSK_LAUNCHED(ctx);
+            pp.in_pay = sb.pay_tmp;
+            pp.out_pay = sb.payv;
+            partition_kernel<2, true><<<grid2, kPartThreads, 0, st>>>(nullptr, sb.part_tmp, nnz, (int)n_mu, sb.offs, tstart, sb.cursor,
+                                                                     sb.keyid, 0, pay_kshift, pp);
+            TTSK_LAUNCHED(ctx);
+            if (pay_done) *pay_done = true;
+            return TTSK_OK;
+        }
+        PayPlan none;
+        std::memset(&none, 0, sizeof(none));
+        partition_kernel<1, false><<<(unsigned)local_grid, kPartThreads, 0, st>>>(key_idx, nullptr, nnz, (int)n_mu, sb.offs, tstart, l1base,
+                                                                                 sb.part_tmp, block_len, 32, none);
         TTSK_LAUNCHED(ctx);
         const unsigned grid = (unsigned)std::min<long long>((nnz + kPartTile - 1) / kPartTile, 4LL * ctx->sm_count);
-        partition_kernel<2><<<grid, kPartThreads, 0, st>>>(nullptr, sb.part_tmp, nnz, (int)n_mu, sb.offs, tstart, sb.cursor, sb.keyid, 0);
+        partition_kernel<2, false><<<grid, kPartThreads, 0, st>>>(nullptr, sb.part_tmp, nnz, (int)n_mu, sb.offs, tstart, sb.cursor, sb.keyid, 0,
+                                                                 32, none);
         TTSK_LAUNCHED(ctx);
         return TTSK_OK;
     }
@@ -858,10 +934,20 @@ static int sparse_chunk(ttsk_ctx* ctx, SparsePlan& pl, int d, const int64_t* sha
             if (!flat_done) TTSK_TRY(launch_last_mode_unbucketed(ctx, P, st, &flat_done));
             if (flat_done) { TTSK_TRY(mark(1)); continue; }
         }
-        TTSK_TRY(sort_keys(ctx, nnz, idx_rows[mu], shape[mu], sb, st, mu));
+        // both factors tabulated: the payload partition + the bulk-copy gather pass (ttsk_sparse_gather.cu)
+        PayPlan pay;
+        int pay_kshift = 32;
+        bool pay_done = false;
+        const bool want_pay = sb.n_modes == 0 && gt_plan(P, has_x, &pay, &pay_kshift);
+        TTSK_TRY(sort_keys(ctx, nnz, idx_rows[mu], shape[mu], sb, st, mu, want_pay ? &pay : nullptr, pay_kshift, &pay_done));
         P.keyid = sb.keyid;
         P.offs = sb.offs;
         TTSK_TRY(mark(0));
+        if (pay_done) {
+            TTSK_TRY(launch_gt(ctx, P, sb.keyid, sb.payv, pay, pay_kshift, st));
+            TTSK_TRY(mark(1));
+            continue;
+        }
         bool gw_done = false;  // warp-autonomous forms (ttsk_sparse_gen.cu) when exactly one source is generated
         if (!has_x) TTSK_TRY(try_launch_gw_direct(ctx, P, st, &gw_done));
         if (!gw_done) TTSK_TRY(try_launch_gw_seg(ctx, P, has_x, st, &gw_done));
