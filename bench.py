@@ -404,7 +404,7 @@ def main():
             "config": config_dict(nnz, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(nnz) if world == 1 else None, "peak_source": which,
-                         "kernel": "ttsk::gw_kernel (modes 0, 2, 3: fused lazy-Gaussian generator) / ttsk::sparse_pass_kernel (mode 1: table-row gather), one launch per mode", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_NNZ * n_loc / n_pass,
+                         "kernel": "ttsk::gw_kernel (modes 0, 2, 3: fused lazy-Gaussian generator) / ttsk::gt_kernel (mode 1: table-row gather on the payload partition, bulk-copy staged), one launch per mode", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_NNZ * n_loc / n_pass,
                          "launches_per_step": n_pass,
                          "note": "algorithmic 40 B/nnz over the d=4 mode passes (10 B/nnz per launch) / summed pass "
                                  "time of the last step; the kernel is FP64-issue-bound (bit-exact ndtri), see "

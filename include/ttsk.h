@@ -57,6 +57,9 @@ int ttsk_memset_zero(ttsk_ctx *ctx, void *d_ptr, int64_t bytes, void *stream);
 int ttsk_sync(ttsk_ctx *ctx, void *stream);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t ttsk_launch_count(ttsk_ctx *ctx);
+/* Account for kernels of this library launched outside its entry points: the replay of a CUDA graph captured around
+ * ttsk_* calls launches the captured kernels again without passing through the counter. */
+int ttsk_note_replayed_launches(ttsk_ctx *ctx, int64_t n);
 /* The library keeps two grow-only device allocations per context: a workspace arena and a cache of
  * Gaussian-DRM prefix tables (DRM state: reused by later sketches with the same DRM, like the
  * reference keeps TT-DRM cores, tt_sketch/drm/tensor_train_drm.py:52-56).  ttsk_set_table_cache_cap
@@ -65,6 +68,9 @@ int64_t ttsk_launch_count(ttsk_ctx *ctx);
  * ttsk_trim releases both allocations (synchronises). */
 int ttsk_set_table_cache_cap(ttsk_ctx *ctx, int64_t bytes);
 int64_t ttsk_table_cache_bytes(ttsk_ctx *ctx);
+/* Counter that changes whenever the context's workspace arena is allocated, grown or released: a CUDA graph captured
+ * around ttsk_* calls holds arena pointers and must be re-captured when it changes. */
+int64_t ttsk_workspace_generation(ttsk_ctx *ctx);
 /* Nonzeros per staging buffer of the host-buffer entry points below (default 2^24; two buffers of
  * 8 (d + 1) bytes per nonzero each).  Inputs longer than this are streamed in chunks. */
 int ttsk_set_stage_nnz(ttsk_ctx *ctx, int64_t nnz);

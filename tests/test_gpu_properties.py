@@ -288,3 +288,64 @@ def test_public_operator_registry_is_the_plug_in_point():
             reg.pop(Shifted, None)
     for a, b in zip(got.Psi_cores + got.Omega_mats, base.Psi_cores + base.Omega_mats):
         assert _close(a, b, tol=1e-12)
+
+
+def test_cuda_graph_replay_of_launch_bound_sketches():
+    """Sketches of TT / CP / dense input are fixed chains of small launches: the second call with the same objects
+    captures the chain into a CUDA graph, later calls replay it.  Replays must equal the eager result bit for bit,
+    count their kernel launches, follow an in-place edit of the input (`invalidate_device()` re-uploads into the same
+    device arrays) and a replaced core; a one-off call never captures."""
+    from tt_sketch import _backend as be
+    from tt_sketch import sketch_dispatch as sd
+    from tt_sketch.drm import TensorTrainDRM
+    from tt_sketch.sketch import hmt_sketch, orthogonal_sketch, stream_sketch
+    from tt_sketch.tensor import CPTensor, TensorTrain
+
+    shape = (7, 8, 9, 10)
+    lr, rr = (3, 4, 5), (5, 6, 7)
+    L = TensorTrainDRM(lr, shape=shape, transpose=False, seed=1)
+    R = TensorTrainDRM(rr, shape=shape, transpose=True, seed=2)
+    for make, call in [(lambda: TensorTrain.random(shape, (4, 5, 3), seed=6),
+                        lambda X: orthogonal_sketch(X, lr, rr, left_drm=L, right_drm=R).cores),
+                       (lambda: CPTensor.random(shape, 6, seed=7),
+                        lambda X: (lambda s: s.Psi_cores + s.Omega_mats)(stream_sketch(X, lr, rr, left_drm=L, right_drm=R))),
+                       (lambda: TensorTrain.random(shape, (4, 5, 3), seed=8) + CPTensor.random(shape, 3, seed=9),
+                        lambda X: hmt_sketch(X, rr, drm=R).cores)]:
+        X = make()
+        sd.use_graphs(False)
+        want = call(X)
+        sd.use_graphs(True)
+        c0 = dict(sd.graph_stats)
+        first = call(X)                       # first sighting: eager
+        assert sd.graph_stats["captured"] == c0["captured"]
+        l0 = be.launch_count()
+        second = call(X)                      # second: capture + replay
+        l1 = be.launch_count()
+        third = call(X)                       # replay only
+        l2 = be.launch_count()
+        assert sd.graph_stats["captured"] == c0["captured"] + 1 and sd.graph_stats["replayed"] >= c0["replayed"] + 2
+        assert l1 - l0 > 0 and l2 - l1 == l1 - l0
+        for got in (first, second, third):
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b)
+        # in-place edit of the host arrays + invalidate: same device arrays, same graph, new numbers
+        parts = X.tensors if hasattr(X, "tensors") else [X]
+        parts[0].cores[1][...] *= 2.0
+        parts[0].invalidate_device()
+        edited = call(X)
+        assert sd.graph_stats["captured"] == c0["captured"] + 1
+        sd.use_graphs(False)
+        want2 = call(X)
+        sd.use_graphs(True)
+        for a, b in zip(edited, want2):
+            assert np.array_equal(a, b)
+        assert not all(np.array_equal(a, b) for a, b in zip(edited, want))
+        # a replaced core of another shape: new device arrays, eager again (no stale replay)
+        if isinstance(parts[0], TensorTrain):
+            r0 = parts[0].cores[0].shape[2]
+            parts[0][0] = np.concatenate([parts[0].cores[0], np.zeros((1, shape[0], 1))], axis=2)
+            parts[0][1] = np.concatenate([parts[0].cores[1], np.zeros((1,) + parts[0].cores[1].shape[1:])], axis=0)
+            assert parts[0].cores[0].shape[2] == r0 + 1
+            again = call(X)
+            for a, b in zip(again, want2):
+                assert _close(a, b, tol=1e-9)

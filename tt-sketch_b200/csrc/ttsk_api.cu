@@ -30,6 +30,7 @@ int axpy_launch(ttsk_ctx* ctx, int64_t n, double alpha, const double* x, double*
 
 int ttsk_ctx::ws_reserve(int64_t bytes) {
     if (bytes <= ws_bytes) return TTSK_OK;
+    ws_gen++;
     if (ws) {
         TTSK_CUDA(cudaDeviceSynchronize());
         TTSK_CUDA(cudaFree(ws));
@@ -181,6 +182,11 @@ int ttsk_sync(ttsk_ctx* ctx, void* stream) {
     return TTSK_OK;
 }
 int64_t ttsk_launch_count(ttsk_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int ttsk_note_replayed_launches(ttsk_ctx* ctx, int64_t n) {
+    TTSK_ARG(ctx != nullptr && n >= 0, "ttsk_note_replayed_launches");
+    ctx->launches += n;
+    return TTSK_OK;
+}
 
 int ttsk_set_table_cache_cap(ttsk_ctx* ctx, int64_t bytes) {
     TTSK_ARG(ctx != nullptr && bytes >= 0, "ttsk_set_table_cache_cap");
@@ -188,6 +194,7 @@ int ttsk_set_table_cache_cap(ttsk_ctx* ctx, int64_t bytes) {
     return TTSK_OK;
 }
 int64_t ttsk_table_cache_bytes(ttsk_ctx* ctx) { return ctx ? ctx->table_bytes : -1; }
+int64_t ttsk_workspace_generation(ttsk_ctx* ctx) { return ctx ? ctx->ws_gen : -1; }
 
 int ttsk_set_stage_nnz(ttsk_ctx* ctx, int64_t nnz) {
     TTSK_ARG(ctx != nullptr && nnz >= 1, "ttsk_set_stage_nnz");
@@ -202,6 +209,7 @@ int ttsk_trim(ttsk_ctx* ctx) {
     if (ctx->ws) TTSK_CUDA(cudaFree(ctx->ws));
     ctx->ws = nullptr;
     ctx->ws_bytes = ctx->ws_used = 0;
+    ctx->ws_gen++;
     for (auto& t : ctx->tables) TTSK_CUDA(cudaFree(t.ptr));
     ctx->tables.clear();
     ctx->table_bytes = 0;

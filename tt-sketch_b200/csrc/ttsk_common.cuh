@@ -59,6 +59,7 @@ struct ttsk_ctx {
     char* ws = nullptr;
     int64_t ws_bytes = 0;
     int64_t ws_used = 0;
+    int64_t ws_gen = 0;  // bumped whenever the arena is (re)allocated or freed: captured CUDA graphs hold arena pointers
     // pinned staging + copy stream for *_host entry points
     void* pinned[2] = {nullptr, nullptr};
     int64_t pinned_bytes = 0;

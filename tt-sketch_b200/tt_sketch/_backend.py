@@ -50,12 +50,14 @@ SIGNATURES = {
     "ttsk_memset_zero": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "ttsk_sync": (c_int, [c_void_p, c_void_p]),
     "ttsk_launch_count": (c_int64, [c_void_p]),
+    "ttsk_note_replayed_launches": (c_int, [c_void_p, c_int64]),
     "ttsk_last_kernel_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "ttsk_last_pass_ms": (c_int, [c_void_p, POINTER(c_double), c_int, POINTER(c_int)]),
     "ttsk_sg_pass_count": (c_int64, [c_void_p]),
     "ttsk_set_table_cache_cap": (c_int, [c_void_p, c_int64]),
     "ttsk_table_cache_bytes": (c_int64, [c_void_p]),
     "ttsk_set_stage_nnz": (c_int, [c_void_p, c_int64]),
+    "ttsk_workspace_generation": (c_int64, [c_void_p]),
     "ttsk_trim": (c_int, [c_void_p]),
     "ttsk_lazy_gaussian": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, POINTER(c_int64), c_int, c_int,
                                    c_uint64, c_void_p, c_void_p]),

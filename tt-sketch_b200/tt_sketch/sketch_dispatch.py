@@ -346,9 +346,9 @@ def streaming_sketch_device(tensor: Tensor, left_drm: DRM, right_drm: DRM, packe
     return packed, (shape, rL, rR)
 
 
-def _sequential_sketch(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, method: SketchMethod):
+def _sequential_device(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, method: SketchMethod):
     """orthogonal / HMT: Psi_mu depends on the QR of Psi_{mu-1}, so bonds are processed in order;
-    all intermediates stay on the device."""
+    all intermediates stay on the device.  Returns (Psi, Omega) as lists of device tensors."""
     shape = tuple(tensor.shape)
     d = len(shape)
     parts = _summands(tensor)
@@ -385,6 +385,112 @@ def _sequential_sketch(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, 
         if mu < d - 1:
             P = orth_step_device(P, Omega[mu] if method == SketchMethod.orthogonal else None)
         Psi.append(P)
+    return Psi, Omega
+
+
+# ------------------------------------------------------------------ CUDA graphs for the sequential loops
+# An orthogonal / HMT sketch of TT / CP / Tucker / dense input is a fixed chain of several hundred small launches
+# (C2: 645) whose cost is the launch path, not the kernels.  The chain depends only on the device arrays of the
+# input and of the DRMs, so it is captured once per (input, DRMs, method) into a CUDA graph and replayed by later
+# calls with the same objects (streaming updates, repeated sketches of one operand).  Sparse summands are excluded:
+# their passes size workspaces from the data.  TTSK_GRAPHS=0 (or `use_graphs(False)`) turns this off.
+import os as _os
+from collections import OrderedDict as _OrderedDict
+
+_USE_GRAPHS = _os.environ.get("TTSK_GRAPHS", "1") != "0"
+_SEQ_GRAPHS: "_OrderedDict" = _OrderedDict()
+_SEQ_GRAPHS_MAX = 8
+graph_stats = {"captured": 0, "replayed": 0, "eager": 0}
+
+
+def use_graphs(flag: bool) -> None:
+    global _USE_GRAPHS
+    _USE_GRAPHS = bool(flag)
+    if not flag:
+        _SEQ_GRAPHS.clear()
+
+
+def _device_ids(x) -> tuple:
+    if isinstance(x, dict):
+        return tuple(_device_ids(v) for v in x.values())
+    if isinstance(x, (list, tuple)):
+        return tuple(_device_ids(v) for v in x)
+    return (id(x),)
+
+
+def _drm_key(drm: Optional[DRM]):
+    if drm is None:
+        return None
+    cores = getattr(drm, "cores", None)
+    mats = getattr(drm, "sketching_mats", None)
+    return (type(drm).__name__, id(drm), int(drm.seed), tuple(drm.rank_min), tuple(drm.rank_max),
+            tuple(id(c) for c in cores) if cores is not None else None,
+            tuple(id(m) for m in mats) if mats is not None else None)
+
+
+def _graphed(kind: str, tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, fn: Callable):
+    """`fn()` (device tensors out) through a cached CUDA graph, or None when the call is not graphable (then the caller
+    runs `fn` eagerly).  A chain is captured the SECOND time its key -- the device arrays of the input, the DRMs, the
+    method -- is seen, so a one-off sketch never pays for a capture; an input that is refreshed in place
+    (`invalidate_device()` + same shapes re-uploads into the same device arrays) keeps its graph."""
+    import torch
+
+    parts = _summands(tensor)
+    if not _USE_GRAPHS or not parts or any(isinstance(X, SparseTensor) or not _is_stock(type(X)) for X in parts):
+        return None
+    dev = [X.device() for X in parts]  # uploads (if any) happen here, outside the capture
+    gen = int(be.lib().ttsk_workspace_generation(be.ctx()))
+    key = (kind, be.device_index(), _device_ids(dev), _drm_key(left_drm), _drm_key(right_drm))
+    ent = _SEQ_GRAPHS.get(key)
+    if ent is None or ent["gen"] != gen:
+        # first sighting (or the workspace arena moved): run eagerly -- this is also the warm-up a capture needs (DRM
+        # cores uploaded, arena at its size, kernel attributes set)
+        _SEQ_GRAPHS[key] = {"gen": None, "graph": None, "seen": 1, "keep": (tensor, left_drm, right_drm, dev)}
+        while len(_SEQ_GRAPHS) > _SEQ_GRAPHS_MAX:
+            _SEQ_GRAPHS.popitem(last=False)
+        out = fn()
+        _SEQ_GRAPHS[key]["gen"] = int(be.lib().ttsk_workspace_generation(be.ctx()))
+        graph_stats["eager"] += 1
+        return out
+    _SEQ_GRAPHS.move_to_end(key)
+    if ent["graph"] is None:
+        if ent.get("failed"):
+            return None
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        before = be.launch_count()
+        try:
+            with torch.cuda.graph(graph):
+                out = fn()
+        except Exception as exc:  # not capturable on this input: remember that and fall back
+            if _os.environ.get("TTSK_DEBUG"):
+                import sys as _sys
+                import traceback as _tb
+                print("[ttsk] CUDA-graph capture failed:", repr(exc), file=_sys.stderr)
+                _tb.print_exc()
+            torch.cuda.synchronize()
+            ent["failed"] = True
+            return None
+        if int(be.lib().ttsk_workspace_generation(be.ctx())) != gen:
+            ent["failed"] = True
+            return None  # the arena moved during the capture: the graph is unusable
+        ent.update(graph=graph, out=out, launches=be.launch_count() - before, fresh=True)
+        graph_stats["captured"] += 1
+    ent["graph"].replay()
+    if ent.pop("fresh", False):
+        pass  # the capture already went through the launch counter once without executing: it stands for this replay
+    else:
+        be.check(be.lib().ttsk_note_replayed_launches(be.ctx(), ent["launches"]))
+    graph_stats["replayed"] += 1
+    return ent["out"]
+
+
+def _sequential_sketch(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, method: SketchMethod):
+    run = partial(_sequential_device, tensor, left_drm, right_drm, method)
+    out = _graphed(method.value, tensor, left_drm, right_drm, run)
+    if out is None:
+        out = run()
+    Psi, Omega = out
     return SketchContainer([be.to_host(p) for p in Psi], [be.to_host(o) for o in Omega])
 
 
@@ -393,6 +499,8 @@ def general_sketch(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, meth
     if method != SketchMethod.hmt and left_drm is None:
         raise ValueError(f"left_drm must be provided for method '{method}'")
     if method == SketchMethod.streaming:
-        packed, (shape, rL, rR) = streaming_sketch_device(tensor, left_drm, right_drm)
+        run = partial(streaming_sketch_device, tensor, left_drm, right_drm)
+        out = _graphed("streaming", tensor, left_drm, right_drm, run)
+        packed, (shape, rL, rR) = out if out is not None else run()
         return SketchContainer.unpack(be.to_host_pinned(packed), shape, rL, rR, copy=False)
     return _sequential_sketch(tensor, left_drm, right_drm, method)

@@ -19,6 +19,27 @@ from numpy.random import SeedSequence
 from tt_sketch.utils import ArrayList, TTRank, process_tt_rank, random_normal
 
 
+def _is_transposed_view(c, pc) -> bool:
+    """`c` is `pc` with its axes reversed, on the same memory (what `.T` of a container hands out)."""
+    return (isinstance(c, np.ndarray) and isinstance(pc, np.ndarray) and c.dtype == pc.dtype
+            and c.shape == pc.shape[::-1] and c.strides == pc.strides[::-1]
+            and c.__array_interface__["data"][0] == pc.__array_interface__["data"][0])
+
+
+def _copy_into(dev_tensors, host_arrays) -> bool:
+    """Host arrays -> existing device tensors of the same shapes (one H2D copy each); False if anything differs."""
+    import torch
+
+    if len(dev_tensors) != len(host_arrays):
+        return False
+    for t, a in zip(dev_tensors, host_arrays):
+        if not isinstance(a, np.ndarray) or tuple(t.shape) != tuple(a.shape) or not t.is_contiguous():
+            return False
+    for t, a in zip(dev_tensors, host_arrays):
+        t.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)))
+    return True
+
+
 class Tensor(ABC):
     shape: Tuple[int, ...]
 
@@ -104,14 +125,23 @@ class Tensor(ABC):
         from tt_sketch import _backend as be
 
         key = (be.device_index(), self._host_arrays_id())
-        if self.__dict__.get("_dev") is None or self.__dict__.get("_dev_key") != key:
-            self.__dict__["_dev"] = self._upload()
+        dev = self.__dict__.get("_dev")
+        if dev is None or self.__dict__.get("_dev_key") != key:
+            slot = self.__dict__.get("_dev_slot")
+            if dev is None or slot != key[0] or not self._refresh_in_place(dev):
+                self.__dict__["_dev"] = self._upload()
             self.__dict__["_dev_key"] = key
+            self.__dict__["_dev_slot"] = key[0]
         return self.__dict__["_dev"]
 
     def invalidate_device(self) -> None:
-        self.__dict__.pop("_dev", None)
+        """The host arrays were edited: the next `.device()` uploads them again -- into the SAME device arrays when the
+        shapes still fit (so CUDA graphs captured on them stay valid), into new ones otherwise."""
         self.__dict__.pop("_dev_key", None)
+
+    def _refresh_in_place(self, dev) -> bool:
+        """Copy the current host arrays into the existing device arrays `dev`; False if that is not possible."""
+        return False
 
     def _device_if_current(self):
         """The cached upload if it still matches the host arrays and the current device, else None."""
@@ -136,7 +166,9 @@ class DenseTensor(Tensor):
 
     @property
     def T(self) -> "DenseTensor":
-        return DenseTensor(np.transpose(self.data))
+        t = DenseTensor(np.transpose(self.data))
+        t.__dict__["_dev_parent"] = self
+        return t
 
     @property
     def size(self) -> int:
@@ -165,9 +197,17 @@ class DenseTensor(Tensor):
     def _host_arrays_id(self):
         return (id(self.data),)
 
+    def _refresh_in_place(self, dev) -> bool:
+        return "_dev_parent" not in self.__dict__ and _copy_into([dev["data"]], [self.data])
+
     def _upload(self):
         from tt_sketch import _backend as be
 
+        parent = self.__dict__.get("_dev_parent")
+        pd = parent._device_if_current() if parent is not None else None
+        if pd is not None and _is_transposed_view(self.data, parent.data):  # transpose of the parent's upload, on the device
+            x = pd["data"]
+            return {"data": x.permute(*reversed(range(x.dim()))).contiguous()}
         return {"data": be.to_device(self.data, np.float64)}
 
 
@@ -375,13 +415,16 @@ class TensorTrain(Tensor):
     def _host_arrays_id(self):
         return tuple(id(c) for c in self.cores)
 
+    def _refresh_in_place(self, dev) -> bool:
+        return "_dev_parent" not in self.__dict__ and _copy_into(dev["cores"], list(self.cores))
+
     def _upload(self):
         from tt_sketch import _backend as be
 
         parent = self.__dict__.get("_dev_parent")
         pd = parent._device_if_current() if parent is not None else None
         if pd is not None and len(parent.cores) == len(self.cores) and \
-                all(getattr(c, "base", None) is pc for c, pc in zip(self.cores, reversed(parent.cores))):
+                all(_is_transposed_view(c, pc) for c, pc in zip(self.cores, reversed(parent.cores))):
             return {"cores": [c.permute(2, 1, 0).contiguous() for c in reversed(pd["cores"])]}
         return {"cores": [be.to_device(c, np.float64) for c in self.cores]}
 
@@ -437,6 +480,9 @@ class CPTensor(Tensor):
     def _host_arrays_id(self):
         return tuple(id(c) for c in self.cores)
 
+    def _refresh_in_place(self, dev) -> bool:
+        return "_dev_parent" not in self.__dict__ and _copy_into(dev["cores"], list(self.cores))
+
     def _upload(self):
         from tt_sketch import _backend as be
 
@@ -460,7 +506,9 @@ class TuckerTensor(Tensor):
 
     @property
     def T(self) -> "TuckerTensor":
-        return TuckerTensor(self.factors[::-1], np.transpose(self.core))
+        t = TuckerTensor(self.factors[::-1], np.transpose(self.core))
+        t.__dict__["_dev_parent"] = self
+        return t
 
     @property
     def size(self) -> int:
@@ -497,9 +545,19 @@ class TuckerTensor(Tensor):
     def _host_arrays_id(self):
         return (id(self.core),) + tuple(id(U) for U in self.factors)
 
+    def _refresh_in_place(self, dev) -> bool:
+        return "_dev_parent" not in self.__dict__ and \
+            _copy_into([dev["core"]] + list(dev["factors"]), [self.core] + list(self.factors))
+
     def _upload(self):
         from tt_sketch import _backend as be
 
+        parent = self.__dict__.get("_dev_parent")
+        pd = parent._device_if_current() if parent is not None else None
+        if pd is not None and _is_transposed_view(self.core, parent.core) and len(self.factors) == len(parent.factors) \
+                and all(a is b for a, b in zip(self.factors, reversed(parent.factors))):
+            c = pd["core"]
+            return {"core": c.permute(*reversed(range(c.dim()))).contiguous(), "factors": list(reversed(pd["factors"]))}
         return {"core": be.to_device(self.core, np.float64),
                 "factors": [be.to_device(U, np.float64) for U in self.factors]}
 
