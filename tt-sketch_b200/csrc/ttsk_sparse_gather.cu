@@ -267,7 +267,12 @@ static int launch_gt_t(ttsk_ctx* ctx, const PassParams& P, const unsigned long l
     G.nnz = P.nnz; G.n_mu = P.n_mu;
     G.words = words; G.vals = reinterpret_cast<const double*>(vals);
     G.A = P.A.base; G.B = P.B.base; G.a_stride = P.A.row_stride; G.b_stride = P.B.row_stride;
-    G.rA = P.rA; G.rB = P.rB; G.pa = tile_pitch(MI); G.pb = tile_pitch(NJ);
+    G.rA = P.rA; G.rB = P.rB; G.pa = tile_pitch(MI);
+    // B fragment loads: lane (g, q) reads row q, column 8 j + g; a half warp (g < 4, all q) is conflict free when the
+    // row pitch is 8 or 24 words (mod 32), i.e. 4 or 12 doubles (mod 16) -- tile_pitch's 8 (mod 16) puts rows q and
+    // q + 2 on the same banks (ncu: 38 % of this kernel's shared wavefronts were conflicts)
+    G.pb = 8 * NJ;
+    while (G.pb % 16 != 4 && G.pb % 16 != 12) G.pb += 2;
     G.kshift = kshift; G.bshift = pay.bshift;
     G.bmask = (1ull << pay.bshift) - 1ull;
     G.amask = (1ull << (kshift - pay.bshift)) - 1ull;
