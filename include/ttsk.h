@@ -228,6 +228,11 @@ int ttsk_khatri_rao(ttsk_ctx *ctx, int64_t n, int64_t R, int64_t r, const double
  * scipy.linalg.lstsq in tt_sketch/utils.py:98-109).  m, n <= 256. */
 int ttsk_pinv(ttsk_ctx *ctx, const double *d_A, int m, int n, double rcond, double *d_pinv,
               void *stream);
+/* Thin SVD A (m, n) = U diag(S) V^T, k = min(m, n) <= 256, max(m, n) <= 65536: U (m, k) row-major (columns times the
+ * singular values when u_times_s), S (k) descending, V^T (k, n) row-major.  Replaces np.linalg.svd in
+ * TensorTrain.round / svdvals, tt_sketch/tensor.py:446-506 (the step after the sketching path). */
+int ttsk_svd(ttsk_ctx *ctx, const double *d_A, int m, int n, double *d_U, double *d_S, double *d_Vt, int u_times_s,
+             void *stream);
 /* In-place economic QR of d_A (m, n) row-major, m >= n, n <= 256: on return d_A holds Q with
  * LAPACK's Householder sign convention (scipy.linalg.qr(mode="economic") in
  * tt_sketch/sketch_dispatch.py:172). */

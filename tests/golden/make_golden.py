@@ -354,12 +354,46 @@ def gen_tucker_dense_gauss():
     print("tucker_dense_gauss.npz:", names)
 
 
+def gen_tt_algebra():
+    """Section 8(f) rank 3: TensorTrain.orthogonalize / round / svdvals / dot / norm / error / gather of the reference
+    (tensor.py:414-609) on a TT whose ranks are inflated by a direct sum (so rounding has something to cut)."""
+    store = {}
+    shape = (7, 8, 9, 10)
+    a = TensorTrain.random(shape, (4, 5, 3), seed=21)
+    b = TensorTrain.random(shape, (2, 3, 2), seed=22)
+    s = a.add(b * 1e-4)                       # ranks (6, 8, 5): the small summand is what eps = 1e-3 removes
+    tensor_pack("a_T", a, store)
+    tensor_pack("b_T", b, store)
+    tensor_pack("s_T", s, store)
+    for i, c in enumerate(s.orthogonalize().cores):
+        store[f"orth_C{i}"] = c
+    for key, kw in (("round_eps", dict(eps=1e-3)), ("round_rank", dict(max_rank=(3, 4, 2))), ("round_exact", dict(eps=1e-12))):
+        r = s.round(**kw)
+        store[key + "_rank"] = np.array(r.rank, dtype=np.int64)
+        store[key + "_dense"] = r.to_numpy()
+    for i, v in enumerate(s.svdvals()):
+        store[f"svdvals{i}"] = v
+    store["dot_ab"] = np.float64(a.dot(b))
+    store["norm_s"] = np.float64(s.norm())
+    store["err_sa"] = np.float64(s.error(a))
+    store["err_sa_rel"] = np.float64(s.error(a, relative=True))
+    rng = np.random.default_rng(23)
+    idx = np.stack([rng.integers(0, n, 64) for n in shape]).astype(np.int64)
+    store["gather_idx"] = idx
+    store["gather_s"] = s.gather(idx)
+    np.savez_compressed(os.path.join(OUT, "tt_algebra.npz"), **store)
+    print("tt_algebra.npz")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "stt_ops":  # later additions leave the earlier fixtures untouched
         gen_stt_ops()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sparse_sign":
         gen_sparse_sign()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "tt_algebra":
+        gen_tt_algebra()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tucker_dense_gauss":
         gen_tucker_dense_gauss()
@@ -370,6 +404,7 @@ if __name__ == "__main__":
     gen_stt_ops()
     gen_sparse_sign()
     gen_tucker_dense_gauss()
+    gen_tt_algebra()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")

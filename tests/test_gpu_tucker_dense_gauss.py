@@ -149,3 +149,55 @@ def test_dense_gaussian_drm_vs_reference_golden():
         assert rel_err(a, b) < TOL
     for a, b in zip(sk.Omega_mats, stored_list(z, "dg_sparse_blocked_Omega")):
         assert rel_err(a, b) < TOL
+
+
+def test_tt_algebra_after_the_sketch_vs_reference_golden():
+    """SURVEY 8(f) rank 3 on the device: TensorTrain.orthogonalize / round / svdvals / dot / norm / error / gather
+    (reference tensor.py:414-609; goldens tests/golden/tt_algebra.npz written by the unmodified reference).  Cores of an
+    orthogonalised / rounded TT are unique only up to signs and rotations, so tensors, ranks, singular values and
+    orthogonality are compared."""
+    from tt_sketch import _backend as be
+
+    z = load("tt_algebra.npz")
+    a, b, s = (make_tensor(tensor_desc(z, k + "_T")) for k in "abs")
+    dense = s.to_numpy()
+    # ---- orthogonalize: same tensor, orthonormal columns, and (LAPACK signs) the reference's cores themselves
+    o = s.orthogonalize()
+    assert o.rank == s.rank
+    assert np.linalg.norm(o.to_numpy() - dense) <= 1e-13 * np.linalg.norm(dense)
+    for i, c in enumerate(o.cores[:-1]):
+        m = c.reshape(-1, c.shape[2])
+        assert np.max(np.abs(m.T @ m - np.eye(m.shape[1]))) < 1e-13
+        assert rel_err(c, z[f"orth_C{i}"]) < 1e-9
+    assert rel_err(o.cores[-1], z[f"orth_C{len(o.cores) - 1}"]) < 1e-9
+    # ---- round: by tolerance, by rank, and at machine precision
+    for key, kw in (("round_eps", dict(eps=1e-3)), ("round_rank", dict(max_rank=(3, 4, 2))), ("round_exact", dict(eps=1e-12))):
+        r = s.round(**kw)
+        assert r.rank == tuple(int(x) for x in z[key + "_rank"]), (key, r.rank)
+        want = z[key + "_dense"]
+        assert np.linalg.norm(r.to_numpy() - want) <= 1e-10 * np.linalg.norm(want), key
+        for c in r.cores[1:]:  # left in right-orthogonal form
+            m = c.reshape(c.shape[0], -1)
+            assert np.max(np.abs(m @ m.T - np.eye(m.shape[0]))) < 1e-12
+    # ---- singular values of the unfoldings
+    sv = s.svdvals()
+    assert len(sv) == 4
+    for i, v in enumerate(sv):
+        want = z[f"svdvals{i}"]
+        assert v.shape == want.shape and np.max(np.abs(v - want)) <= 1e-12 * want[0]
+    # ---- scalars
+    assert abs(a.dot(b) - float(z["dot_ab"])) <= 1e-13 * max(1.0, abs(float(z["dot_ab"])))
+    assert abs(s.norm() - float(z["norm_s"])) <= 1e-13 * float(z["norm_s"])
+    assert abs(s.error(a) - float(z["err_sa"])) <= 1e-9 * float(z["err_sa"])
+    assert abs(s.error(a, relative=True) - float(z["err_sa_rel"])) <= 1e-9 * float(z["err_sa_rel"])
+    assert rel_err(s.gather(z["gather_idx"]), z["gather_s"]) < 1e-13
+    # ---- ttsk_svd itself, tall and wide, against NumPy
+    rng = np.random.default_rng(0)
+    for m, n in ((40, 7), (6, 90), (33, 33)):
+        A = rng.standard_normal((m, n))
+        U, S, Vt = (be.to_host(t) for t in be.svd(be.to_device(A)))
+        assert np.max(np.abs(S - np.linalg.svd(A, compute_uv=False))) < 1e-13 * S[0]
+        assert np.max(np.abs((U * S) @ Vt - A)) < 1e-13 * S[0]
+        assert np.max(np.abs(U.T @ U - np.eye(len(S)))) < 1e-13 and np.max(np.abs(Vt @ Vt.T - np.eye(len(S)))) < 1e-13
+        US = be.to_host(be.svd(be.to_device(A), u_times_s=True)[0])
+        assert np.max(np.abs(US - U * S)) < 1e-13 * S[0]

@@ -24,9 +24,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 // W: (rows, c) stored COLUMN-major (W[j*rows + i]); V: (c, c) column-major.
 // One-sided Jacobi with a round-robin tournament: in each round c/2 disjoint column pairs are
 // rotated concurrently, one warp per pair.
+// With `pinv == nullptr` the factors are written instead (ttsk_svd): singular values in descending order to
+// svd_S (c), U (m, c) row-major to svd_U -- its columns multiplied by the singular values when u_times_s -- and
+// V^T (c, n) row-major to svd_Vt.
 __global__ void __launch_bounds__(1024) jacobi_pinv_kernel(const double* __restrict__ A, int m, int n, double rcond,
                                                           double* __restrict__ W, double* __restrict__ V,
-                                                          double* __restrict__ sig, double* __restrict__ pinv) {
+                                                          double* __restrict__ sig, double* __restrict__ pinv,
+                                                          double* __restrict__ svd_U, double* __restrict__ svd_S,
+                                                          double* __restrict__ svd_Vt, int u_times_s,
+                                                          int* __restrict__ perm) {
     const bool tall = m >= n;
     const int rows = tall ? m : n, c = tall ? n : m;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -99,6 +105,33 @@ __global__ void __launch_bounds__(1024) jacobi_pinv_kernel(const double* __restr
         s_max = mx;
     }
     __syncthreads();
+    if (pinv == nullptr) {
+        if (tid == 0) {  // descending order of the singular values (c <= 256: a selection sort by one thread)
+            for (int j = 0; j < c; j++) perm[j] = j;
+            for (int a = 0; a < c; a++) {
+                int best = a;
+                for (int b = a + 1; b < c; b++)
+                    if (sig[perm[b]] > sig[perm[best]]) best = b;
+                const int t = perm[a]; perm[a] = perm[best]; perm[best] = t;
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < c; j += blockDim.x) svd_S[j] = sig[perm[j]];
+        // tall: A = (W / s) S V^T;  wide: A^T = (W / s) S V^T  =>  A = V S (W / s)^T
+        for (int e = tid; e < m * c; e += blockDim.x) {
+            const int i = e / c, jj = e - i * c, j = perm[jj];
+            const double sj = sig[j];
+            double u = tall ? (sj > 0.0 ? W[(long long)j * rows + i] / sj : 0.0) : V[(long long)j * c + i];
+            if (u_times_s) u = tall ? W[(long long)j * rows + i] : u * sj;
+            svd_U[e] = u;
+        }
+        for (long long e = tid; e < (long long)c * n; e += blockDim.x) {
+            const int jj = (int)(e / n), i = (int)(e - (long long)jj * n), j = perm[jj];
+            const double sj = sig[j];
+            svd_Vt[e] = tall ? V[(long long)j * c + i] : (sj > 0.0 ? W[(long long)j * rows + i] / sj : 0.0);
+        }
+        return;
+    }
     const double cut = (rcond < 0.0 ? DBL_EPSILON : rcond) * s_max;
     // pinv (n, m) row-major
     for (int e = tid; e < n * m; e += blockDim.x) {
@@ -358,7 +391,30 @@ extern "C" int ttsk_pinv(ttsk_ctx* ctx, const double* d_A, int m, int n, double 
     double* W = (double*)ctx->ws_alloc((int64_t)rows * c * 8);
     double* V = (double*)ctx->ws_alloc((int64_t)c * c * 8);
     double* sig = (double*)ctx->ws_alloc((int64_t)c * 8);
-    ttsk::jacobi_pinv_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_A, m, n, rcond, W, V, sig, d_pinv);
+    ttsk::jacobi_pinv_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_A, m, n, rcond, W, V, sig, d_pinv, nullptr, nullptr, nullptr, 0,
+                                                                   nullptr);
+    TTSK_LAUNCHED(ctx);
+    return TTSK_OK;
+}
+
+// Thin SVD A (m, n) = U diag(S) V^T with k = min(m, n) <= 256 columns (one-sided Jacobi, one CTA; S descending).
+// Replaces np.linalg.svd in TensorTrain.round / svdvals (reference tensor.py:446-506): the validation step after a
+// sketch, not a throughput kernel.
+extern "C" int ttsk_svd(ttsk_ctx* ctx, const double* d_A, int m, int n, double* d_U, double* d_S, double* d_Vt,
+                        int u_times_s, void* stream) {
+    TTSK_ARG(ctx != nullptr, "ctx is NULL");
+    TTSK_ARG(m >= 1 && n >= 1 && m <= 65536 && n <= 65536 && (m <= 256 || n <= 256), "svd: min(m, n) must be <= 256");
+    TTSK_ARG(d_A && d_U && d_S && d_Vt, "NULL pointer");
+    const int rows = m >= n ? m : n, c = m >= n ? n : m;
+    const int64_t need = ((int64_t)rows * c + (int64_t)c * c + 2 * c) * 8 + 2048;
+    TTSK_TRY(ctx->ws_reserve(need));
+    ctx->ws_reset();
+    double* W = (double*)ctx->ws_alloc((int64_t)rows * c * 8);
+    double* V = (double*)ctx->ws_alloc((int64_t)c * c * 8);
+    double* sig = (double*)ctx->ws_alloc((int64_t)c * 8);
+    int* perm = (int*)ctx->ws_alloc((int64_t)c * 4);
+    TTSK_ARG(W && V && sig && perm, "svd: workspace");
+    ttsk::jacobi_pinv_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_A, m, n, -1.0, W, V, sig, nullptr, d_U, d_S, d_Vt, u_times_s, perm);
     TTSK_LAUNCHED(ctx);
     return TTSK_OK;
 }

@@ -18,7 +18,7 @@
 
 namespace ttsk {
 
-constexpr int kGtTN = 64, kGtConsumers = 8, kGtProducers = 8, kGtThreads = 32 * (kGtConsumers + kGtProducers), kGtMaxStages = 8;
+constexpr int kGtTN = 96, kGtConsumers = 12, kGtProducers = 4, kGtThreads = 32 * (kGtConsumers + kGtProducers), kGtMaxStages = 8;
 
 struct GtParams {
     long long nnz, n_mu;

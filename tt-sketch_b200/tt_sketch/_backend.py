@@ -89,6 +89,7 @@ SIGNATURES = {
                                 c_void_p]),
     "ttsk_pinv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
     "ttsk_qr_q": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "ttsk_svd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
 }
 
 _lib = None
@@ -259,6 +260,17 @@ def pinv(A, rcond: float = -1.0):
     out = empty((n, m))
     check(lib().ttsk_pinv(ctx(), ptr(A), m, n, rcond, ptr(out), stream()))
     return out
+
+
+def svd(A, u_times_s: bool = False):
+    """Thin SVD of a device matrix (min(m, n) <= 256): (U or U*S, S descending, Vt) as device tensors."""
+    if not A.is_contiguous():
+        A = A.contiguous()
+    m, n = A.shape
+    k = min(m, n)
+    U, S, Vt = empty((m, k)), empty((k,)), empty((k, n))
+    check(lib().ttsk_svd(ctx(), ptr(A), m, n, ptr(U), ptr(S), ptr(Vt), 1 if u_times_s else 0, stream()))
+    return U, S, Vt
 
 
 def qr_q_inplace(A):

@@ -396,13 +396,123 @@ class TensorTrain(Tensor):
         return be.to_host(v).reshape(-1)
 
     def dot(self, other, reverse: bool = False) -> float:
-        """TT . TT in a left-to-right sweep (reference tensor.py:542-560); anything else through the base class."""
+        """TT . TT in a left-to-right sweep on the device (reference tensor.py:542-560: two GEMMs per mode);
+        anything else through the base class."""
         if isinstance(other, TensorTrain):
-            res = np.einsum("ijk,ljm->km", self.cores[0], other.cores[0])
-            for c1, c2 in zip(self.cores[1:], other.cores[1:]):
-                res = np.einsum("ij,ika,jkb->ab", res, c1, c2, optimize="optimal")
-            return float(np.sum(res))
+            from tt_sketch import _backend as be
+
+            mine, theirs = self.device()["cores"], other.device()["cores"]
+            res = None
+            for c1, c2 in zip(mine, theirs):
+                r1, n, a = c1.shape
+                r2, _, b = c2.shape
+                if res is None:
+                    res = be.gemm(c1.reshape(n, a).T, c2.reshape(n, b))                  # (a, b)
+                else:
+                    w = be.gemm(res.T, c1.reshape(r1, n * a))                            # (r2, n * a)
+                    res = be.gemm(w.reshape(r2 * n, a).T, c2.reshape(r2 * n, b))         # (a, b)
+            return float(be.to_host(res).sum())
         return super().dot(other, reverse=reverse)
+
+    # ---- the step after the sketch: orthogonalisation, rounding, norms of TTs (reference tensor.py:442-609) on the
+    # device: QR by ttsk_qr_q (LAPACK's Householder signs, so Q equals np.linalg.qr's), R = Q^T A and the core
+    # updates by ttsk_gemm, SVDs by ttsk_svd (one-sided Jacobi).
+    def orthogonalize(self) -> "TensorTrain":
+        """QR sweep: every core but the last gets orthonormal columns as an (r n, r') matrix (reference :562-575)."""
+        from tt_sketch import _backend as be
+
+        cores = self.device()["cores"]
+        new, R = [], None
+        for mu, C in enumerate(cores):
+            r0, n, r1 = C.shape
+            if R is not None:
+                C = be.gemm(R, C.reshape(r0, n * r1))
+                r0 = C.shape[0]
+            A = C.reshape(r0 * n, r1)
+            if mu == len(cores) - 1:
+                new.append(A.reshape(r0, n, r1))
+                break
+            m = r0 * n
+            k = min(m, r1)
+            Q = A[:, :k].clone() if k < r1 else A.clone()   # a wide unfolding: Q of its leading square block
+            be.qr_q_inplace(Q)
+            R = be.gemm(Q.T, A)
+            new.append(Q.reshape(r0, n, k))
+        return TensorTrain([be.to_host(c) for c in new])
+
+    def norm(self) -> float:
+        return float(np.linalg.norm(self.orthogonalize().cores[-1]))
+
+    def add(self, other: "TensorTrain") -> "TensorTrain":
+        """Direct sum of the cores (reference :519-540); `+` stays the lazy TensorSum."""
+        cores = [np.concatenate((self.cores[0], other.cores[0]), axis=2)]
+        for a, b in zip(self.cores[1:-1], other.cores[1:-1]):
+            blk = np.zeros((a.shape[0] + b.shape[0], a.shape[1], a.shape[2] + b.shape[2]))
+            blk[: a.shape[0], :, : a.shape[2]] = a
+            blk[a.shape[0]:, :, a.shape[2]:] = b
+            cores.append(blk)
+        cores.append(np.concatenate((self.cores[-1], other.cores[-1]), axis=0))
+        return TensorTrain(cores)
+
+    def _rl_svd_sweep(self, eps, max_rank, orthogonalized: bool, keep_cores: bool):
+        from tt_sketch import _backend as be
+
+        tt = self if orthogonalized else self.orthogonalize()
+        cores = tt.device()["cores"]
+        d = len(cores)
+        new, svals, US = [], [], None
+        for mu in range(d - 1, -1, -1):
+            C = cores[mu]
+            r0, n, r1 = C.shape
+            if US is not None:
+                C = be.gemm(C.reshape(r0 * n, r1), US).reshape(r0, n, US.shape[1])
+                r1 = C.shape[2]
+            if mu > 0:
+                U, S, Vt = be.svd(C.reshape(r0, n * r1), u_times_s=True)
+                s_host = be.to_host(S)
+                svals.append(s_host)
+                r = len(s_host) if eps is None else max(1, min(int(np.sum(s_host > s_host[0] * eps)), int(max_rank[mu - 1])))
+                US = U[:, :r]
+                if keep_cores:
+                    new.append(be.to_host(Vt[:r]).reshape(r, n, r1))
+            else:
+                if keep_cores:
+                    new.append(be.to_host(C))
+                else:  # svdvals of the first unfolding (r0 n, r1)
+                    svals.append(be.to_host(be.svd(C.reshape(r0 * n, r1))[1]))
+        return new[::-1], svals[::-1]
+
+    def round(self, eps: Optional[float] = None, max_rank=None, orthogonalized: bool = False) -> "TensorTrain":
+        """TT-SVD rounding: left-orthogonalise, then truncate in a right-to-left SVD sweep (reference :446-484;
+        singular values above eps * s_max are kept, at most max_rank)."""
+        if eps is None:
+            eps = 0
+        if max_rank is None:
+            max_rank = self.rank
+        max_rank = process_tt_rank(max_rank, self.shape, trim=True)
+        cores, _ = self._rl_svd_sweep(eps, max_rank, orthogonalized, keep_cores=True)
+        return TensorTrain(cores)
+
+    def svdvals(self):
+        """Singular values of every unfolding (reference :486-506)."""
+        return self._rl_svd_sweep(None, None, False, keep_cores=False)[1]
+
+    def error(self, other, relative: bool = False, rmse: bool = False, fast: bool = False) -> float:
+        """Against another TT (or anything with `to_tt`): ||self - other|| from the orthogonalised difference, exact
+        without densifying (reference :577-609); otherwise the generic rule."""
+        if hasattr(other, "to_tt") and not isinstance(other, TensorTrain):
+            other = other.to_tt()
+        if isinstance(other, TensorTrain):
+            err = self.add(-other).norm()
+            if relative:
+                on = other.norm()
+                if on == 0:
+                    return float("inf")
+                err /= on
+            if rmse:
+                err /= float(np.sqrt(np.prod(self.shape)))
+            return float(err)
+        return super().error(other, relative=relative, rmse=rmse, fast=fast)
 
     def __mul__(self, other: float) -> "TensorTrain":
         cores = [c.copy() for c in self.cores]
