@@ -238,6 +238,15 @@ int ttsk_svd(ttsk_ctx *ctx, const double *d_A, int m, int n, double *d_U, double
  * tt_sketch/sketch_dispatch.py:172). */
 int ttsk_qr_q(ttsk_ctx *ctx, double *d_A, int64_t m, int n, void *stream);
 
+/* ---- FROSTT ".tns" text -> COO (host code; the on-disk format in front of the sketching path).  Replaces the
+ * per-line Python loop of scripts/frostt.py:51-66 of the reference.  One nonzero per line: d 1-based integer coordinates and
+ * a value, blank separated; empty lines and lines starting with '#' are skipped.
+ * ttsk_tns_count: number of data lines in buf[0, len) (or -1) and, in *d_out, the order read off the first one.
+ * ttsk_tns_parse: fills idx (d rows of nnz int64, 0-based: the layout of ttsk_sparse_sketch_host), val (nnz) and
+ * max_idx (d: largest 0-based coordinate per mode); nnz must equal ttsk_tns_count.  Multi-threaded. */
+int64_t ttsk_tns_count(const char *buf, int64_t len, int *d_out);
+int ttsk_tns_parse(const char *buf, int64_t len, int d, int64_t nnz, int64_t *idx, double *val, int64_t *max_idx);
+
 #ifdef __cplusplus
 }
 #endif

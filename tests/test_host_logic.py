@@ -243,3 +243,51 @@ def test_tucker_tensor_container_semantics():
     assert np.allclose((2.5 * X).to_numpy(), 2.5 * dense, atol=1e-13)
     Y = TuckerTensor.random((6, 7, 8), (2, 9, 3), seed=5)
     assert np.array_equal(X.core, Y.core) and all(np.array_equal(a, b) for a, b in zip(X.factors, Y.factors))
+
+
+def test_frostt_tns_ingestion(tmp_path):
+    """FROSTT .tns(.gz) text -> COO through the native parser (reference scripts/frostt.py:51-89): indices 0-based,
+    values parsed like Python's float(), comments / blank lines / CRLF / trailing blanks tolerated, the .npz cache,
+    and the error cases."""
+    import gzip
+
+    from tt_sketch.frostt import get_frostt_tensor, parse_tns, process_frostt_tensor
+
+    rng = np.random.default_rng(7)
+    shape = (37, 5, 1200, 9)
+    n = 50_000
+    idx = np.stack([rng.integers(1, s + 1, n) for s in shape])
+    vals = rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, n)
+    texts = ["%.17g" % v if i % 3 else ("%e" % v if i % 2 else repr(float(v))) for i, v in enumerate(vals)]
+    lines = ["# a comment", ""]
+    for i in range(n):
+        sep = " " if i % 5 else "\t"
+        lines.append(sep.join(str(int(x)) for x in idx[:, i]) + sep + texts[i] + ("  " if i % 7 == 0 else "") + ("\r" if i % 11 == 0 else ""))
+    body = ("\n".join(lines) + "\n").encode()
+    want_vals = np.array([float(t) for t in texts])
+    got_idx, got_val, mx = parse_tns(body)
+    assert got_idx.shape == (4, n) and np.array_equal(got_idx, idx - 1)
+    assert np.array_equal(got_val.view(np.uint64), want_vals.view(np.uint64))
+    assert np.array_equal(mx, idx.max(axis=1) - 1)
+    assert np.array_equal(parse_tns(body[:-1])[1], got_val)       # no newline at the end of the file
+    for name, opener in (("t.tns.gz", gzip.open), ("u.tns", open)):
+        path = tmp_path / name
+        with opener(path, "wb") as f:
+            f.write(body)
+        X = process_frostt_tensor(str(path), nnz=n, shape=shape)
+        assert X.shape == shape and X.nnz == n and np.array_equal(X.indices, idx - 1) and np.array_equal(X.entries, want_vals)
+    assert process_frostt_tensor(str(tmp_path / "u.tns")).shape == tuple(int(m) for m in idx.max(axis=1))
+    Y = get_frostt_tensor("https://example.org/frostt/t.tns.gz", n, shape, data_dir=str(tmp_path))
+    assert (tmp_path / "t.tns.npz").exists() and np.array_equal(Y.entries, want_vals)
+    (tmp_path / "t.tns.gz").unlink()                               # second call: served from the cache
+    Z = get_frostt_tensor("t.tns.gz", n, shape, data_dir=str(tmp_path))
+    assert Z.shape == shape and np.array_equal(Z.indices, idx - 1)
+    with pytest.raises(FileNotFoundError):
+        get_frostt_tensor("missing.tns.gz", data_dir=str(tmp_path))
+    with pytest.raises(ValueError):
+        parse_tns(body, nnz=n + 1)
+    for bad in (b"1 2 3\n1 2 x\n", b"0 1 2.0\n", b"1 2 3.0\n1 2\n", b"# only a comment\n"):
+        with pytest.raises(ValueError):
+            parse_tns(bad)
+    with pytest.raises(ValueError):
+        process_frostt_tensor(str(tmp_path / "u.tns"), shape=(3, 3, 3, 3))

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libttsk.so")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["ttsk_sparse_pass_x0.cu", "ttsk_sparse_pass_x1.cu", "ttsk_sparse_gen.cu", "ttsk_sparse_gather.cu", "ttsk_api.cu", "ttsk_gauss.cu", "ttsk_gemm.cu", "ttsk_sparse.cu",
-           "ttsk_linalg.cu", "ttsk_tt.cu", "ttsk_dense.cu"]
+           "ttsk_linalg.cu", "ttsk_tt.cu", "ttsk_dense.cu", "ttsk_tns.cu"]
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

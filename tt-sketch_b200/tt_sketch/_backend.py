@@ -89,6 +89,8 @@ SIGNATURES = {
                                 c_void_p]),
     "ttsk_pinv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
     "ttsk_qr_q": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "ttsk_tns_count": (c_int64, [c_char_p, c_int64, c_void_p]),
+    "ttsk_tns_parse": (c_int, [c_char_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "ttsk_svd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
 }
 
