@@ -97,11 +97,11 @@ def _flatten(tensor: Tensor) -> List[Tensor]:
 def _gpu_local_sketch(part: Optional[Tensor], left_drm, right_drm, total: int):
     """Packed partial sketch of this rank's shard as a device tensor (the production path)."""
     from tt_sketch import _backend as be
-    from tt_sketch.sketch_dispatch import streaming_sketch_device
+    from tt_sketch.sketch_dispatch import streaming_sketch
 
     if part is None:
         return be.zeros(total)
-    packed, _ = streaming_sketch_device(part, left_drm, right_drm)
+    packed, _ = streaming_sketch(part, left_drm, right_drm)
     return packed
 
 
@@ -223,7 +223,7 @@ def allreduce_blocked_stream_sketch(local_tensor: Tensor, left_drm, right_drm, l
 
     from tt_sketch import _backend as be
     from tt_sketch.sketch import _assemble_blocked_stream_sketches, merged_block_drms
-    from tt_sketch.sketch_dispatch import streaming_sketch_device
+    from tt_sketch.sketch_dispatch import streaming_sketch as streaming_sketch_device
 
     on = dist.is_initialized() and dist.get_world_size(group) > 1
     check_same_drms(left_drm, right_drm, group)

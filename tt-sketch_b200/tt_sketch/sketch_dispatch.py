@@ -423,7 +423,9 @@ def _drm_key(drm: Optional[DRM]):
         return None
     cores = getattr(drm, "cores", None)
     mats = getattr(drm, "sketching_mats", None)
-    return (type(drm).__name__, id(drm), int(drm.seed), tuple(drm.rank_min), tuple(drm.rank_max),
+    # by content, not by object: a rank slice made for one call (blocked sketches) shares its parent's core arrays
+    return (type(drm).__name__, bool(drm.transpose), int(drm.seed), tuple(drm.shape), tuple(drm.rank_min),
+            tuple(drm.rank_max), tuple(drm.true_rank),
             tuple(id(c) for c in cores) if cores is not None else None,
             tuple(id(m) for m in mats) if mats is not None else None)
 
@@ -494,13 +496,31 @@ def _sequential_sketch(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, 
     return SketchContainer([be.to_host(p) for p in Psi], [be.to_host(o) for o in Omega])
 
 
+def streaming_sketch(tensor: Tensor, left_drm: DRM, right_drm: DRM):
+    """`streaming_sketch_device` with the launch-bound summands (TT / CP / Tucker / dense: one fixed chain of small
+    launches each) replayed as ONE CUDA graph and the sparse summands accumulated into its output buffer afterwards
+    (C5: 100 TT summands next to a sparse term).  The returned packed buffer is overwritten by the next call with the
+    same operands: consume it (copy to the host, all-reduce, unpack) before sketching again."""
+    parts = _summands(tensor)
+    fixed = [X for X in parts if not isinstance(X, SparseTensor) and _is_stock(type(X))]
+    if not fixed or not _USE_GRAPHS:
+        return streaming_sketch_device(tensor, left_drm, right_drm)
+    sub = fixed[0] if len(fixed) == 1 else TensorSum(fixed, shape=tuple(tensor.shape))
+    run = partial(streaming_sketch_device, sub, left_drm, right_drm)
+    out = _graphed("streaming", sub, left_drm, right_drm, run)
+    packed, meta = out if out is not None else run()
+    rest = [X for X in parts if not any(X is F for F in fixed)]
+    if rest:
+        streaming_sketch_device(rest[0] if len(rest) == 1 else TensorSum(rest, shape=tuple(tensor.shape)), left_drm, right_drm,
+                                packed=packed)
+    return packed, meta
+
+
 def general_sketch(tensor: Tensor, left_drm: Optional[DRM], right_drm: DRM, method: SketchMethod) -> SketchContainer:
     """Sketch `tensor` with the given DRMs; returns host arrays in a SketchContainer."""
     if method != SketchMethod.hmt and left_drm is None:
         raise ValueError(f"left_drm must be provided for method '{method}'")
     if method == SketchMethod.streaming:
-        run = partial(streaming_sketch_device, tensor, left_drm, right_drm)
-        out = _graphed("streaming", tensor, left_drm, right_drm, run)
-        packed, (shape, rL, rR) = out if out is not None else run()
+        packed, (shape, rL, rR) = streaming_sketch(tensor, left_drm, right_drm)
         return SketchContainer.unpack(be.to_host_pinned(packed), shape, rL, rR, copy=False)
     return _sequential_sketch(tensor, left_drm, right_drm, method)
