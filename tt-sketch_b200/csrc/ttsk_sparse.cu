@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(kPartThreads) partition_kernel(const long long
     __shared__ int s_tot[kPartBins];
     __shared__ int s_loc[kPartBins];
     __shared__ unsigned long long s_out[kPartTile];
+    extern __shared__ unsigned long long s_pay[];  // PAY: the values' tile buffer (kPartTile words of dynamic shared memory)
     __shared__ long long s_range[2];
     __shared__ int s_bucket;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -353,7 +354,6 @@ __global__ void __launch_bounds__(kPartThreads) partition_kernel(const long long
         __syncthreads();
         // the tile in digit order in shared memory, then out in runs: consecutive threads write consecutive words of
         // a run (a lane-per-element scatter costs one L2 sector write per word, the limit of these sweeps)
-        int pos[PAY ? kPartPer : 1];
 #pragma unroll
         for (int u = 0; u < kPartPer; u++) {
             if (w[u] != ~0ull) {
@@ -361,12 +361,11 @@ __global__ void __launch_bounds__(kPartThreads) partition_kernel(const long long
                 const int dgt = (LEVEL == 1) ? (key >> 7) : (key & (kPartBins - 1));
                 const int at = s_loc[dgt] + s_wcnt[warp][dgt] + rank[u];
                 s_out[at] = w[u];
-                if (PAY) pos[u] = at;
+                if (PAY) s_pay[at] = pay[u];  // the values take the same route through their own tile buffer
             }
         }
         __syncthreads();
         const int n_here = (int)(hi - lo);
-        int dst[PAY ? kPartPer : 1];
 #pragma unroll
         for (int u = 0; u < kPartPer; u++) {
             const int i = tid + u * kPartThreads;
@@ -376,22 +375,10 @@ __global__ void __launch_bounds__(kPartThreads) partition_kernel(const long long
                 const int dgt = (LEVEL == 1) ? (key >> 7) : (key & (kPartBins - 1));
                 const int at = s_base[dgt] + (i - s_loc[dgt]);
                 out_words[at] = x;
-                if (PAY) dst[u] = at;
+                if (PAY) pp.out_pay[at] = s_pay[i];
             }
         }
         __syncthreads();
-        if (PAY) {  // the values take the same route through the tile buffer
-#pragma unroll
-            for (int u = 0; u < kPartPer; u++)
-                if (w[u] != ~0ull) s_out[pos[u]] = pay[u];
-            __syncthreads();
-#pragma unroll
-            for (int u = 0; u < kPartPer; u++) {
-                const int i = tid + u * kPartThreads;
-                if (i < n_here) pp.out_pay[dst[u]] = s_out[i];
-            }
-            __syncthreads();
-        }
     }
 }
 
@@ -683,12 +670,15 @@ static int sort_keys(ttsk_ctx* ctx, int64_t nnz, const long long* key_idx, int64
             PayPlan pp = *pay;
             pp.in_pay = nullptr;
             pp.out_pay = sb.pay_tmp;
-            partition_kernel<1, true><<<(unsigned)local_grid, kPartThreads, 0, st>>>(key_idx, nullptr, nnz, (int)n_mu, sb.offs, tstart,
+            const size_t pay_smem = (size_t)kPartTile * 8;
+            TTSK_CUDA(cudaFuncSetAttribute(partition_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pay_smem));
+            TTSK_CUDA(cudaFuncSetAttribute(partition_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pay_smem));
+            partition_kernel<1, true><<<(unsigned)local_grid, kPartThreads, pay_smem, st>>>(key_idx, nullptr, nnz, (int)n_mu, sb.offs, tstart,
                                                                                     l1base, sb.part_tmp, block_len, pay_kshift, pp);
             TTSK_LAUNCHED(ctx);
             pp.in_pay = sb.pay_tmp;
             pp.out_pay = sb.payv;
-            partition_kernel<2, true><<<grid2, kPartThreads, 0, st>>>(nullptr, sb.part_tmp, nnz, (int)n_mu, sb.offs, tstart, sb.cursor,
+            partition_kernel<2, true><<<grid2, kPartThreads, pay_smem, st>>>(nullptr, sb.part_tmp, nnz, (int)n_mu, sb.offs, tstart, sb.cursor,
                                                                      sb.keyid, 0, pay_kshift, pp);
             TTSK_LAUNCHED(ctx);
             if (pay_done) *pay_done = true;
