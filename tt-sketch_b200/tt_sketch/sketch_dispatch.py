@@ -302,10 +302,24 @@ def _fusable_tt(X: Tensor, left_drm: DRM, right_drm: DRM) -> bool:
             and tuple(left_drm.shape) == tuple(X.shape) == tuple(right_drm.shape))
 
 
+_warned_wide_rank = False
+
+
 def _fusable(X: Tensor, left_drm: DRM, right_drm: DRM) -> bool:
-    return (isinstance(X, SparseTensor) and type(left_drm) in (SparseGaussianDRM, TensorTrainDRM)
-            and type(right_drm) in (SparseGaussianDRM, TensorTrainDRM)
-            and max(max(left_drm.rank), max(right_drm.rank)) <= 64 and X.nnz > 0)
+    global _warned_wide_rank
+    if not (isinstance(X, SparseTensor) and type(left_drm) in (SparseGaussianDRM, TensorTrainDRM)
+            and type(right_drm) in (SparseGaussianDRM, TensorTrainDRM) and X.nnz > 0):
+        return False
+    if max(max(left_drm.rank), max(right_drm.rank)) > 64:
+        if not _warned_wide_rank:  # say so once: the operator-level path materialises (rank x nnz) DRM matrices
+            import warnings
+
+            warnings.warn("tt_sketch: a DRM rank above 64 takes the operator-level sparse path (DRM contractions "
+                          "materialised as (rank x nnz) device arrays) instead of the fused sparse kernels",
+                          RuntimeWarning, stacklevel=3)
+            _warned_wide_rank = True
+        return False
+    return True
 
 
 def streaming_sketch_device(tensor: Tensor, left_drm: DRM, right_drm: DRM, packed=None):
