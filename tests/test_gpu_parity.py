@@ -292,3 +292,31 @@ def test_sparse_sign_drm_bit_exact_and_sketch_vs_golden():
     part = [be.to_host(m) for m in sl.sketch_sparse_device(X)]
     for mu, (lo, hi) in enumerate(zip((1, 1, 2), (3, 4, 5))):
         assert np.array_equal(part[mu], full[mu][lo:hi])
+
+
+@pytest.mark.parametrize("shape,lr,rr", [((300, 200, 50), (6, 8), (10, 4)),
+                                         ((40, 30, 20, 10, 8), (4, 6, 8, 2), (8, 12, 6, 4)),
+                                         ((5000, 3000, 700, 9), (20, 20, 20), (40, 40, 40))])
+def test_gather_pass_on_payload_partition_vs_oracle(oracle_lib, shape, lr, rr):
+    """Modes whose two factors are both prefix tables take the payload partition + bulk-copy gather pass
+    (csrc/ttsk_sparse_gather.cu): orders 3, 4, 5, one very long segment, duplicates -- against the oracle."""
+    from oracle.sketch_oracle import Drm
+    from tt_sketch import _backend as be
+    from tt_sketch.sketch_dispatch import SketchMethod, general_sketch
+
+    nnz = 150_000
+    _, idx, val = _c4_like(nnz, seed=len(shape), shape=shape)
+    idx[1, :40_000] = 7          # one long segment in the gather mode
+    idx[:, 1000:1100] = idx[:, :100]  # duplicates
+    d = len(shape)
+    oL = Drm("gauss", False, shape, (0,) * (d - 1), lr, 41)
+    oR = Drm("gauss", True, shape, (0,) * (d - 1), rr, 42)
+    desc = ("sparse", shape, idx, val)
+    Psi, Om = oracle_lib.general_sketch(desc, oL, oR, "streaming", fast_sparse=True)
+    before = be.lib().ttsk_sg_pass_count(be.ctx())
+    sk = general_sketch(make_tensor(desc), make_drm(oL), make_drm(oR), SketchMethod.streaming)
+    assert be.lib().ttsk_sg_pass_count(be.ctx()) > before
+    for a, b in zip(sk.Psi_cores, Psi):
+        assert rel_err(a, b) < TOL
+    for a, b in zip(sk.Omega_mats, Om):
+        assert rel_err(a, b) < TOL

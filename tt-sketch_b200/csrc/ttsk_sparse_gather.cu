@@ -305,6 +305,7 @@ static int launch_gt_t(ttsk_ctx* ctx, const PassParams& P, const unsigned long l
                 nst, G.stage_bytes, smem, per_sm, grid, kshift, pay.bshift);
     kern<<<(unsigned)grid, kGtThreads, smem, st>>>(G);
     TTSK_LAUNCHED(ctx);
+    ctx->sg_passes++;  // counted with the other specialised pass forms (ttsk_sg_pass_count): tests assert the form ran
     return TTSK_OK;
 }
 
