@@ -3,10 +3,13 @@
 // Replaces the NumPy einsum / matmul calls of tt_sketch/drm/tensor_train_drm.py:71-122,
 // tt_sketch/sketching_methods/{tensor_train,cp,dense}_sketch.py.
 //
-// Shapes here are (r x n*r)-like with r = 10..100: far too small for tcgen05 (no FP64 kind
-// anyway) -- the work is bound by launch latency and by streaming the one large operand
-// once, so the kernel is a plain shared-memory tiled DFMA kernel whose grid is widened by
-// split-K until it covers the 148 SMs.
+// Shapes here are (r x n*r)-like with r = 10..100 in FP64: tcgen05 has no FP64 kind, the FP64 tensor
+// instruction is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  The work is bound by launch latency and by
+// streaming the one large operand once, so the kernel is a shared-memory tiled DMMA kernel (a CTA
+// computes a 64 x 32 tile, 16 x 32 for skinny M; tile pitches == 4 (mod 16) so the fragment loads are
+// conflict free; arbitrary element strides, so transposes / slices / unfoldings are views) whose grid
+// is widened by split-K until it covers the 148 SMs.  Chains of these launches are replayed as CUDA
+// graphs by the host side (sketch_dispatch._graphed).
 #include <algorithm>
 
 #include "ttsk_common.cuh"
